@@ -1,0 +1,132 @@
+/*
+ * xotb200.h — C ABI of libxotb200.so: the B200-native (sm_100a) shard-decode engine.
+ *
+ * This is the drop-in boundary for xotorch's ONE hot path: the per-shard Llama-style decode/prefill step behind
+ * `InferenceEngine.infer_tensor` and the inter-shard hidden-state hop behind `PeerHandle.send_tensor`.
+ * The reference is pure Python and has no FFI for this path; the closest precedent is the external "Cheetah"
+ * C++ service it talks to over a Unix socket (/root/reference/xotorch/inference/cheetah/sharded_inference_engine.py:331-457).
+ * Each entry point below cites the reference interface it replaces (paths relative to /root/reference).
+ * The ctypes binding a maintainer would add is xotorch_b200/_lib.py (shown in INTEGRATION.md).
+ *
+ * Conventions: every function returns 0 on success or a negative XOTB200_E* code; the message is available
+ * from xotb200_last_error() (thread-local).  All pointers are plain host pointers unless the name says `dev`.
+ * Host buffers are caller-owned; device buffers are library-owned.  No torch types cross this boundary.
+ * Calls on one engine must be serialised by the caller (the reference funnels all engine work through a
+ * 1-thread executor: xotorch/inference/torch/sharded_inference_engine.py:46).
+ */
+#ifndef XOTB200_H
+#define XOTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XOTB200_OK 0
+#define XOTB200_EINVAL (-1)   /* bad argument / wrong state               */
+#define XOTB200_ECUDA (-2)    /* a CUDA runtime call failed               */
+#define XOTB200_EIO (-3)      /* safetensors / file problem               */
+#define XOTB200_ESTRICT (-4)  /* strict loader: tensor missing or unknown */
+#define XOTB200_ETIMEOUT (-5) /* device-side wait on a peer flag expired  */
+
+#define XOTB200_DTYPE_BF16 0
+#define XOTB200_DTYPE_F16 1 /* reserved: 70B fp16 config */
+
+#define XOTB200_ROPE_PLAIN 0  /* RotaryPositionalEmbeddings (general_mha.py:57-63, and llama ids w/o rope_scaling: App. B3) */
+#define XOTB200_ROPE_LLAMA3 1 /* Llama3ScaledRoPE (general_mha.py:33-40)                                              */
+
+/* Mirror of the dict built by load_model_config (xotorch/inference/llm_utils.py:79-126). */
+typedef struct xotb200_model_cfg {
+  int32_t n_layers;       /* num_layers       <- num_hidden_layers        */
+  int32_t dim;            /* embed_dim        <- hidden_size              */
+  int32_t ffn;            /* intermediate_dim <- intermediate_size        */
+  int32_t n_heads;        /* num_heads                                     */
+  int32_t n_kv_heads;     /* num_kv_heads                                  */
+  int32_t head_dim;       /* head_dim (64 or 128)                          */
+  int32_t vocab;          /* vocab_size                                    */
+  int32_t max_pos;        /* max_seq_len      <- max_position_embeddings   */
+  float rope_theta;       /* rope_base                                     */
+  float norm_eps;         /* norm_eps                                      */
+  int32_t tie_embeddings; /* tied lm_head (general_mha.py:42-44,125-126)  */
+  int32_t dtype;          /* XOTB200_DTYPE_*                               */
+  int32_t rope_kind;      /* XOTB200_ROPE_*                                */
+  float rope_factor;      /* HF rope_scaling.factor (App. B2)              */
+  float rope_low_freq_factor;
+  float rope_high_freq_factor;
+  int32_t rope_old_context_len;
+} xotb200_model_cfg;
+
+typedef struct xotb200_engine xotb200_engine;
+
+/* Thread-local message of the last failing call on this thread. */
+const char* xotb200_last_error(void);
+/* Library / build identification ("xotb200 <version> sm_100a"). */
+const char* xotb200_version(void);
+
+/* ---- lifetime: replaces ShardedGeneralModel.__init__ / clear_model
+ *      (xotorch/inference/torch/models/general_mha.py:144-176; sharded_inference_engine.py:85-106) ---- */
+int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** out);
+int xotb200_destroy(xotb200_engine* e);
+
+/* ---- shard selection + weights: replaces TorchDynamicShardInferenceEngine.ensure_shard -> start_model ->
+ *      load_model_weights_torchtune (sharded_inference_engine.py:372-421; llm_utils.py:185-333).
+ *      Inclusive layer range as in Shard (xotorch/inference/shard.py:4-39).  Embedding is held only by the first
+ *      shard, final norm + lm_head only by the last (App. B6).  The loader is STRICT (App. B6). ---- */
+int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer);
+/* set_shard + read every *.safetensors in `dir` (HF names, HF layout; q/k re-laid out like _permute, llm_utils.py:175-183) */
+int xotb200_load_shard(xotb200_engine* e, const char* safetensors_dir, int start_layer, int end_layer);
+/* one tensor by HF name from a host buffer (bf16 bits); tensors outside the shard are ignored (returns 1) */
+int xotb200_load_tensor(xotb200_engine* e, const char* hf_name, const void* host_data, const int64_t* shape, int ndim);
+/* fill the current shard with the counter-based synthetic weights of xotorch_b200/synth.py, generated on device */
+int xotb200_init_synthetic(xotb200_engine* e, uint64_t seed);
+/* 0 if every tensor of the current shard has been loaded, else XOTB200_ESTRICT (message lists the first missing) */
+int xotb200_check_loaded(xotb200_engine* e);
+
+/* ---- request state: replaces encode()'s state/KV reset + setup_cache
+ *      (sharded_inference_engine.py:71-83,133-147) and ShardTransformerDecoder.setup_caches/reset_caches
+ *      (llm_utils.py:369-414).  KV capacity comes from the request (App. B7). ---- */
+int xotb200_begin_request(xotb200_engine* e, int max_total_len);
+
+/* ---- the step: replaces infer_tensor -> ShardedGeneralModel.generate -> ShardTransformerDecoder.forward
+ *      (sharded_inference_engine.py:230-370; general_mha.py:178-254; llm_utils.py:416-489).
+ *      Exactly one of tokens / hidden_f32 is non-NULL (ndim==2 ids vs ndim==3 hidden, sharded_inference_engine.py:254-263).
+ *      n_tokens >= 1 positions starting at pos0 (pos0==0 => prefill).  Output, to caller-owned host memory:
+ *        non-last shard: out_f32[n_tokens*dim]  = hidden state after the shard's last layer (bf16 values widened);
+ *        last shard    : out_f32[vocab]         = logits of the LAST position (bf16 values widened), and the
+ *                        lowest-index argmax is stored for xotb200_last_token(). ---- */
+int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidden_f32, int n_tokens, int pos0,
+                    float* out_f32);
+/* lowest-index argmax of the most recent last-shard logits (on-device "greedy"; sharded_inference_engine.py:208-228 at temp 0) */
+int xotb200_last_token(xotb200_engine* e, int32_t* token);
+
+/* ---- device-resident ring (replaces Node.forward_tensor -> PeerHandle.send_tensor per token:
+ *      xotorch/orchestration/node.py:424-443; xotorch/networking/grpc/grpc_peer_handle.py:111-130) ----
+ * Every engine owns an inbox in its own HBM.  A shard's last kernel stores its bf16 hidden state (or, on the last
+ * shard, the argmax token id) straight into the NEXT engine's inbox over NVLink and releases a flag; the next
+ * shard's first kernel acquires the flag.  No host involvement per token. */
+#define XOTB200_IPC_HANDLE_BYTES 64
+int xotb200_inbox_export(xotb200_engine* e, void* ipc_handle_out /* XOTB200_IPC_HANDLE_BYTES */);
+int xotb200_link_next_ipc(xotb200_engine* e, const void* ipc_handle /* of the next engine's inbox */);
+int xotb200_link_next_local(xotb200_engine* e, xotb200_engine* next); /* same process (may be e itself) */
+/* Hand the result of the most recent xotb200_forward (hidden state of its last position, or last token) to the
+ * next engine's inbox as step `step` — used once after prefill to seed the ring. */
+int xotb200_post_to_next(xotb200_engine* e, int step);
+/* Enqueue n_steps ring steps (CUDA graph replays) starting at ring step `step0`, position `pos0`; asynchronous. */
+int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0);
+/* Wait for the engine's stream; on the last shard copies the n_steps generated token ids (int32) to tokens_out
+ * (may be NULL).  ms_out (may be NULL) = device time of the launched steps by CUDA events. */
+int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float* ms_out);
+/* Per-step device timestamps (globaltimer ns) of the most recent ring run: t_in = input flag observed,
+ * t_out = result posted.  Arrays of n_steps uint64 each (hop latency accounting). */
+int xotb200_ring_timestamps(xotb200_engine* e, uint64_t* t_in, uint64_t* t_out, int n_steps);
+
+/* ---- introspection ---- */
+int xotb200_kernel_launches(xotb200_engine* e, int64_t* count); /* kernels launched by this engine so far */
+int xotb200_weight_bytes(xotb200_engine* e, int64_t* bytes);    /* resident weight bytes of the current shard */
+int xotb200_step_bytes(xotb200_engine* e, int ctx, int64_t* bytes); /* algorithmic HBM bytes of one decode step at context ctx */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XOTB200_H */

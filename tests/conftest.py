@@ -1,0 +1,30 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+  sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+  config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def _has_gpu() -> bool:
+  try:
+    import torch
+    return torch.cuda.is_available()
+  except Exception:
+    return False
+
+
+def pytest_collection_modifyitems(config, items):
+  if _has_gpu():
+    return
+  skip = pytest.mark.skip(reason="no CUDA device in this container")
+  for item in items:
+    if "gpu" in item.keywords:
+      item.add_marker(skip)

@@ -1,0 +1,887 @@
+// engine.cu — host side of libxotb200.so: engine object, weight layout + strict loader, request state, the step
+// launcher (direct mode and CUDA-graph ring mode) and the C ABI declared in include/xotb200.h.
+//
+// HBM layout of a shard (all bf16, 256-byte aligned, execution order so one decode step walks HBM linearly):
+//   per layer: attn_norm[D] | Wqkv[(Hq+2Hkv)*hd, D] | Wo[D, Hq*hd] | mlp_norm[D] | Wgu[2F, D] | Wdown[D, F]
+//     Wqkv rows: q heads then k heads in interleaved-pair order (the reference's `_permute`,
+//       /root/reference/xotorch/inference/llm_utils.py:175-183) so a RoPE pair is two ADJACENT rows and the rotation
+//       fuses into the GEMV epilogue; v rows unchanged.
+//     Wgu rows: gate_m, up_m interleaved so SwiGLU fuses into the epilogue.
+//   first shard: embed[V, D];  last shard: final_norm[D] | lm_head[V, D] (aliases embed when tied).
+//   KV cache: [local_layer][k|v][Hkv][L][hd] (same [Hkv, L, hd] order as torchtune KVCache).
+#include <cuda_runtime.h>
+#include <dirent.h>
+#include <fcntl.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/xotb200.h"
+#include "kernels.cuh"
+
+using namespace xb;
+
+// --------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+#define CK(call)                                                                                            \
+  do {                                                                                                      \
+    cudaError_t _e = (call);                                                                                \
+    if (_e != cudaSuccess) {                                                                                \
+      set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+      return XOTB200_ECUDA;                                                                                 \
+    }                                                                                                       \
+  } while (0)
+#define REQUIRE(cond, ...)                \
+  do {                                    \
+    if (!(cond)) {                        \
+      set_err(__VA_ARGS__);               \
+      return XOTB200_EINVAL;              \
+    }                                     \
+  } while (0)
+
+struct TensorSlot {
+  bf16* dst;        // base of the destination matrix
+  int rows, K;      // HF shape [rows, K] (1-D tensors: rows=1)
+  int mode;         // 0 identity, 1 q/k interleave
+  int stride, off;  // destination row = off + r*stride
+  int tensor_id;    // synth.py tensor id
+  float std, mean;
+  bool loaded;
+};
+
+struct LayerW {
+  bf16 *attn_norm, *wqkv, *wo, *mlp_norm, *wgu, *wdown;
+};
+
+struct GemvCfg {
+  int tr, tk, stages;
+  size_t smem;
+};
+
+struct xotb200_engine {
+  xotb200_model_cfg cfg;
+  int device = 0, sm_count = 148;
+  int start = -1, end = -1;
+  bool first = false, last = false;
+  bf16* blob = nullptr;
+  size_t blob_bytes = 0;
+  std::vector<LayerW> layers;
+  bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
+  std::map<std::string, TensorSlot> slots;
+  // request state
+  bf16* kv = nullptr;
+  int L = 0;
+  float2* rope = nullptr;
+  int rope_len = 0;
+  // activations / scratch
+  bf16 *x = nullptr, *q = nullptr, *attn_out = nullptr, *act = nullptr;
+  float* logits = nullptr;
+  float *part_ml = nullptr, *part_acc = nullptr;
+  unsigned int* tickets = nullptr;  // [Hkv] attention + [1] step end
+  float* cta_best_val = nullptr;
+  int* cta_best_idx = nullptr;
+  int nsplit = 1;
+  StepCtl* ctl = nullptr;
+  InboxHdr* inbox = nullptr;
+  InboxHdr* next_inbox = nullptr;
+  bool next_ipc = false;
+  int* tokens_log = nullptr;
+  unsigned long long *t_in = nullptr, *t_out = nullptr;
+  // staging for the host-buffer API
+  int stage_cap = 0;
+  int* stage_tokens = nullptr;
+  float* stage_f32 = nullptr;
+  bf16 *stage_in = nullptr, *stage_out = nullptr;
+  bool have_result = false;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t ring_graph = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  int last_ring_steps = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// --------------------------------------------------------------------------------------------------------------
+// kernel dispatch
+// --------------------------------------------------------------------------------------------------------------
+typedef void (*gemv_fn)(const GemvArgs);
+
+template <int PRO, int EPI>
+static gemv_fn pick_gemv(int tr, int tk) {
+  if (tr == 2 && tk == 2048) return gemv_kernel<2, 2048, PRO, EPI>;
+  if (tr == 4 && tk == 1024) return gemv_kernel<4, 1024, PRO, EPI>;
+  if (tr == 2 && tk == 1024) return gemv_kernel<2, 1024, PRO, EPI>;
+  if (tr == 4 && tk == 512) return gemv_kernel<4, 512, PRO, EPI>;
+  if (tr == 2 && tk == 512) return gemv_kernel<2, 512, PRO, EPI>;
+  return nullptr;
+}
+static gemv_fn pick_gemv_dyn(int pro, int epi, int tr, int tk) {
+  if (pro == PRO_NORM && epi == EPI_QKV) return pick_gemv<PRO_NORM, EPI_QKV>(tr, tk);
+  if (pro == PRO_PLAIN && epi == EPI_RESID) return pick_gemv<PRO_PLAIN, EPI_RESID>(tr, tk);
+  if (pro == PRO_NORM && epi == EPI_SWIGLU) return pick_gemv<PRO_NORM, EPI_SWIGLU>(tr, tk);
+  if (pro == PRO_NORM && epi == EPI_HEAD) return pick_gemv<PRO_NORM, EPI_HEAD>(tr, tk);
+  return nullptr;
+}
+
+static const size_t SMEM_BUDGET = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
+
+// Choose the tile shape for an [N, K] GEMV on `grid` CTAs: K-chunk = largest of {2048,1024,512} dividing K,
+// rows-per-tile in {2,4} minimising the row imbalance across CTAs (8 KiB stages preferred).
+static GemvCfg choose_gemv(int N, int K, int grid, bool need_pairs) {
+  GemvCfg best{};
+  double best_score = -1;
+  const int cands[5][2] = {{4, 1024}, {2, 2048}, {2, 1024}, {4, 512}, {2, 512}};
+  for (auto& c : cands) {
+    const int tr = c[0], tk = c[1];
+    if (K % tk != 0 || N % tr != 0) continue;
+    (void)need_pairs;
+    const int groups = N / tr;
+    const int maxg = (groups + grid - 1) / grid;
+    double eff = (double)groups / ((double)grid * maxg);
+    const size_t stage = (size_t)tr * tk * 2;
+    const size_t fixed = (size_t)K * 2 + 1024;
+    int stages = (int)((SMEM_BUDGET - fixed) / (NW * stage));
+    if (stages < 2) continue;
+    if (stages > 8) stages = 8;
+    // prefer larger copies / fewer x re-reads on near ties
+    double score = eff + 1e-3 * (tk / 2048.0) + 5e-4 * (tr / 4.0);
+    if (score > best_score) {
+      best_score = score;
+      best.tr = tr;
+      best.tk = tk;
+      best.stages = stages;
+      best.smem = (size_t)NW * stages * stage + (size_t)K * 2 + (size_t)NW * stages * 8 + 128;
+    }
+  }
+  return best;
+}
+
+static int launch_gemv(xotb200_engine* e, int pro, int epi, GemvArgs& a, cudaStream_t st) {
+  const int grid = std::min(e->sm_count, a.N / 2);
+  GemvCfg c = choose_gemv(a.N, a.K, grid, true);
+  REQUIRE(c.tr != 0, "no GEMV tile shape for N=%d K=%d (K must be a multiple of 512, N of 2)", a.N, a.K);
+  gemv_fn fn = pick_gemv_dyn(pro, epi, c.tr, c.tk);
+  REQUIRE(fn != nullptr, "no GEMV instantiation pro=%d epi=%d tr=%d tk=%d", pro, epi, c.tr, c.tk);
+  a.stages = c.stages;
+  {
+    static std::map<std::pair<int, void*>, size_t> attr_done;   // (device, kernel) -> opted-in smem
+    auto key = std::make_pair(e->device, (void*)fn);
+    auto it = attr_done.find(key);
+    if (it == attr_done.end() || it->second < c.smem) {
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+      attr_done[key] = c.smem;
+    }
+  }
+  fn<<<grid, GEMV_THREADS, c.smem, st>>>(a);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+template <int HD>
+static int launch_attn_hd(xotb200_engine* e, const AttnArgs& a, int R, cudaStream_t st) {
+  dim3 grid(e->nsplit, e->cfg.n_kv_heads);
+  switch (R) {
+    case 1: attn_decode_kernel<HD, 1><<<grid, 128, 0, st>>>(a); break;
+    case 2: attn_decode_kernel<HD, 2><<<grid, 128, 0, st>>>(a); break;
+    case 4: attn_decode_kernel<HD, 4><<<grid, 128, 0, st>>>(a); break;
+    case 8: attn_decode_kernel<HD, 8><<<grid, 128, 0, st>>>(a); break;
+    default: set_err("unsupported GQA ratio %d", R); return XOTB200_EINVAL;
+  }
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+// One step of the shard.  ring: inputs from the inbox / outputs to the next inbox, position from ctl.
+// direct: position given, input row `s` of the staging buffers; `do_head` only on the last shard.
+static int launch_step(xotb200_engine* e, bool ring, int pos, int s, bool do_head, cudaStream_t st) {
+  const xotb200_model_cfg& c = e->cfg;
+  const int D = c.dim, F = c.ffn, Hq = c.n_heads, Hkv = c.n_kv_heads, hd = c.head_dim;
+  const int nl = e->end - e->start + 1;
+  {
+    IngestArgs ia{};
+    ia.ctl = e->ctl; ia.inbox = e->inbox; ia.embed = e->first ? e->embed : nullptr; ia.x = e->x; ia.D = D;
+    ia.direct = ring ? 0 : 1; ia.pos = pos;
+    ia.src_token = (!ring && e->first) ? e->stage_tokens + s : nullptr;
+    ia.src_hidden = (!ring && !e->first) ? e->stage_in + (size_t)s * D : nullptr;
+    ia.t_in = e->t_in;
+    ingest_kernel<<<1, 256, 0, st>>>(ia);
+    CK(cudaGetLastError());
+    e->launches++;
+  }
+  for (int li = 0; li < nl; ++li) {
+    const LayerW& w = e->layers[li];
+    bf16* kc = e->kv + ((size_t)li * 2 + 0) * Hkv * e->L * hd;
+    bf16* vc = e->kv + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
+    GemvArgs a{};
+    // qkv
+    a.W = w.wqkv; a.N = (Hq + 2 * Hkv) * hd; a.K = D; a.x_in = e->x; a.norm_w = w.attn_norm; a.eps = c.norm_eps;
+    a.ctl = e->ctl; a.q_out = e->q; a.k_cache = kc; a.v_cache = vc; a.rope = e->rope; a.q_rows = Hq * hd;
+    a.kv_rows = Hkv * hd; a.hd = hd; a.L = e->L;
+    if (int rc = launch_gemv(e, PRO_NORM, EPI_QKV, a, st)) return rc;
+    // attention
+    AttnArgs aa{};
+    aa.q = e->q; aa.k_cache = kc; aa.v_cache = vc; aa.out = e->attn_out; aa.part_ml = e->part_ml;
+    aa.part_acc = e->part_acc; aa.tickets = e->tickets; aa.ctl = e->ctl; aa.L = e->L;
+    aa.scale = 1.0f / sqrtf((float)hd);
+    int rc = hd == 128 ? launch_attn_hd<128>(e, aa, Hq / Hkv, st) : launch_attn_hd<64>(e, aa, Hq / Hkv, st);
+    if (rc) return rc;
+    // o-proj + residual
+    GemvArgs o{};
+    o.W = w.wo; o.N = D; o.K = Hq * hd; o.x_in = e->attn_out; o.ctl = e->ctl; o.res = e->x; o.out = e->x;
+    if ((rc = launch_gemv(e, PRO_PLAIN, EPI_RESID, o, st))) return rc;
+    // gate/up + SwiGLU
+    GemvArgs g{};
+    g.W = w.wgu; g.N = 2 * F; g.K = D; g.x_in = e->x; g.norm_w = w.mlp_norm; g.eps = c.norm_eps; g.ctl = e->ctl;
+    g.out = e->act;
+    if ((rc = launch_gemv(e, PRO_NORM, EPI_SWIGLU, g, st))) return rc;
+    // down + residual (last layer of a non-last shard in ring mode: also store to the next inbox + release flag)
+    GemvArgs d{};
+    d.W = w.wdown; d.N = D; d.K = F; d.x_in = e->act; d.ctl = e->ctl; d.res = e->x; d.out = e->x;
+    if (ring && li == nl - 1 && !e->last) {
+      d.out_peer = reinterpret_cast<bf16*>(reinterpret_cast<char*>(e->next_inbox) + sizeof(InboxHdr));
+      d.final_kernel = 1;
+      d.end.ticket = e->tickets + Hkv; d.end.ctl = e->ctl; d.end.post_flag = e->next_inbox->flag_hidden;
+      d.end.advance = 1; d.end.t_out = e->t_out;
+    }
+    if ((rc = launch_gemv(e, PRO_PLAIN, EPI_RESID, d, st))) return rc;
+  }
+  if (e->last && (ring || do_head)) {
+    GemvArgs h{};
+    h.W = e->lm_head; h.N = c.vocab; h.K = D; h.x_in = e->x; h.norm_w = e->final_norm; h.eps = c.norm_eps;
+    h.ctl = e->ctl; h.logits = e->logits; h.cta_best_val = e->cta_best_val; h.cta_best_idx = e->cta_best_idx;
+    h.tokens_out = e->tokens_log; h.final_kernel = 1;
+    h.end.ticket = e->tickets + Hkv; h.end.ctl = e->ctl; h.end.t_out = e->t_out;
+    if (ring) {
+      h.next_token = e->next_inbox->token;
+      h.end.post_flag = e->next_inbox->flag_token;
+      h.end.advance = 1;
+    }
+    if (int rc = launch_gemv(e, PRO_NORM, EPI_HEAD, h, st)) return rc;
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// minimal JSON (safetensors header) parser
+// --------------------------------------------------------------------------------------------------------------
+struct StEntry {
+  std::string dtype;
+  std::vector<int64_t> shape;
+  int64_t begin = 0, end = 0;
+};
+struct JsonP {
+  const char* p;
+  const char* e;
+  bool ok = true;
+  void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+  bool eat(char c) { ws(); if (p < e && *p == c) { ++p; return true; } return false; }
+  std::string str() {
+    ws();
+    std::string s;
+    if (p >= e || *p != '"') { ok = false; return s; }
+    ++p;
+    while (p < e && *p != '"') {
+      if (*p == '\\' && p + 1 < e) { ++p; }
+      s.push_back(*p++);
+    }
+    if (p < e) ++p; else ok = false;
+    return s;
+  }
+  int64_t num() {
+    ws();
+    char* q = nullptr;
+    long long v = strtoll(p, &q, 10);
+    if (q == p) ok = false;
+    p = q;
+    return v;
+  }
+  void skip() {  // skip any value
+    ws();
+    if (p >= e) { ok = false; return; }
+    if (*p == '"') { str(); return; }
+    if (*p == '{') { ++p; if (eat('}')) return; do { str(); if (!eat(':')) { ok = false; return; } skip(); } while (ok && eat(',')); if (!eat('}')) ok = false; return; }
+    if (*p == '[') { ++p; if (eat(']')) return; do { skip(); } while (ok && eat(',')); if (!eat(']')) ok = false; return; }
+    while (p < e && *p != ',' && *p != '}' && *p != ']') ++p;
+  }
+};
+
+static bool parse_st_header(const char* s, size_t n, std::map<std::string, StEntry>& out) {
+  JsonP j{s, s + n};
+  if (!j.eat('{')) return false;
+  if (j.eat('}')) return true;
+  do {
+    std::string name = j.str();
+    if (!j.ok || !j.eat(':')) return false;
+    if (name == "__metadata__") { j.skip(); continue; }
+    if (!j.eat('{')) return false;
+    StEntry en;
+    do {
+      std::string k = j.str();
+      if (!j.eat(':')) return false;
+      if (k == "dtype") en.dtype = j.str();
+      else if (k == "shape") {
+        if (!j.eat('[')) return false;
+        if (!j.eat(']')) { do { en.shape.push_back(j.num()); } while (j.eat(',')); if (!j.eat(']')) return false; }
+      } else if (k == "data_offsets") {
+        if (!j.eat('[')) return false;
+        en.begin = j.num(); if (!j.eat(',')) return false; en.end = j.num(); if (!j.eat(']')) return false;
+      } else j.skip();
+    } while (j.ok && j.eat(','));
+    if (!j.eat('}')) return false;
+    out[name] = en;
+  } while (j.ok && j.eat(','));
+  return j.ok && j.eat('}');
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// helpers
+// --------------------------------------------------------------------------------------------------------------
+static void free_shard(xotb200_engine* e) {
+  if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
+  if (e->blob) { cudaFree(e->blob); e->blob = nullptr; }
+  if (e->kv) { cudaFree(e->kv); e->kv = nullptr; }
+  e->layers.clear();
+  e->slots.clear();
+  e->embed = e->final_norm = e->lm_head = nullptr;
+  e->start = e->end = -1;
+  e->L = 0;
+}
+
+static int upload_slot(xotb200_engine* e, TensorSlot& s, const void* host) {
+  const size_t bytes = (size_t)s.rows * s.K * 2;
+  if (s.mode == 0 && s.stride == 1) {
+    CK(cudaMemcpyAsync(s.dst + (size_t)s.off * s.K, host, bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  } else {
+    bf16* tmp = nullptr;
+    CK(cudaMalloc(&tmp, bytes));
+    cudaError_t er = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, e->stream);
+    if (er == cudaSuccess) {
+      relayout_rows_kernel<<<s.rows, 128, 0, e->stream>>>(tmp, s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off);
+      er = cudaGetLastError();
+      e->launches++;
+    }
+    cudaError_t er2 = cudaStreamSynchronize(e->stream);
+    cudaFree(tmp);
+    CK(er);
+    CK(er2);
+  }
+  s.loaded = true;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* xotb200_last_error(void) { return g_err; }
+const char* xotb200_version(void) { return "xotb200 0.1.0 sm_100a"; }
+
+int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** out) {
+  REQUIRE(cfg && out, "null argument");
+  REQUIRE(cfg->dtype == XOTB200_DTYPE_BF16, "only bf16 weights are implemented (dtype=%d)", cfg->dtype);
+  REQUIRE(cfg->head_dim == 64 || cfg->head_dim == 128, "head_dim must be 64 or 128 (got %d)", cfg->head_dim);
+  REQUIRE(cfg->n_heads % cfg->n_kv_heads == 0, "n_heads %% n_kv_heads != 0");
+  const int R = cfg->n_heads / cfg->n_kv_heads;
+  REQUIRE(R == 1 || R == 2 || R == 4 || R == 8, "GQA ratio %d unsupported", R);
+  REQUIRE(cfg->dim % 512 == 0 && cfg->ffn % 512 == 0 && (cfg->n_heads * cfg->head_dim) % 512 == 0,
+          "dim, ffn and n_heads*head_dim must be multiples of 512");
+  REQUIRE(cfg->vocab % 4 == 0, "vocab must be a multiple of 4");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  REQUIRE(prop.major == 10, "libxotb200 is sm_100a-only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  xotb200_engine* e = new xotb200_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  const int D = cfg->dim, Hq = cfg->n_heads, Hkv = cfg->n_kv_heads, hd = cfg->head_dim;
+  e->nsplit = std::max(1, std::min(32, e->sm_count / Hkv));
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&e->ev0));
+  CK(cudaEventCreate(&e->ev1));
+  CK(cudaMalloc(&e->x, (size_t)D * 2));
+  CK(cudaMalloc(&e->q, (size_t)Hq * hd * 2));
+  CK(cudaMalloc(&e->attn_out, (size_t)Hq * hd * 2));
+  CK(cudaMalloc(&e->act, (size_t)cfg->ffn * 2));
+  CK(cudaMalloc(&e->logits, (size_t)cfg->vocab * 4));
+  CK(cudaMalloc(&e->part_ml, (size_t)Hq * e->nsplit * 2 * 4));
+  CK(cudaMalloc(&e->part_acc, (size_t)Hq * e->nsplit * hd * 4));
+  CK(cudaMalloc(&e->tickets, (Hkv + 1) * 4));
+  CK(cudaMemset(e->tickets, 0, (Hkv + 1) * 4));
+  CK(cudaMalloc(&e->cta_best_val, 1024 * 4));
+  CK(cudaMalloc(&e->cta_best_idx, 1024 * 4));
+  CK(cudaMalloc(&e->ctl, sizeof(StepCtl)));
+  CK(cudaMemset(e->ctl, 0, sizeof(StepCtl)));
+  const size_t inbox_bytes = sizeof(InboxHdr) + (size_t)2 * D * 2;
+  CK(cudaMalloc(&e->inbox, inbox_bytes));
+  CK(cudaMemset(e->inbox, 0, inbox_bytes));
+  CK(cudaMalloc(&e->tokens_log, MAX_RING_STEPS * 4));
+  CK(cudaMalloc(&e->t_in, MAX_RING_STEPS * 8));
+  CK(cudaMalloc(&e->t_out, MAX_RING_STEPS * 8));
+  CK(cudaMemset(e->t_in, 0, MAX_RING_STEPS * 8));
+  CK(cudaMemset(e->t_out, 0, MAX_RING_STEPS * 8));
+  *out = e;
+  return 0;
+}
+
+int xotb200_destroy(xotb200_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  free_shard(e);
+  if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
+  void* ptrs[] = {e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
+                  e->cta_best_idx, e->ctl, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
+                  e->stage_f32, e->stage_in, e->stage_out};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return 0;
+}
+
+int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer) {
+  REQUIRE(e, "null engine");
+  const xotb200_model_cfg& c = e->cfg;
+  REQUIRE(0 <= start_layer && start_layer <= end_layer && end_layer < c.n_layers, "bad layer range [%d, %d] of %d",
+          start_layer, end_layer, c.n_layers);
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  free_shard(e);
+  e->start = start_layer;
+  e->end = end_layer;
+  e->first = start_layer == 0;
+  e->last = end_layer == c.n_layers - 1;
+  const size_t D = c.dim, F = c.ffn, Hq = c.n_heads, Hkv = c.n_kv_heads, hd = c.head_dim, V = c.vocab;
+  const size_t nl = end_layer - start_layer + 1;
+  const size_t A = 256;
+  const size_t sz_norm = align_up(D * 2, A), sz_qkv = align_up((Hq + 2 * Hkv) * hd * D * 2, A),
+               sz_o = align_up(D * Hq * hd * 2, A), sz_gu = align_up(2 * F * D * 2, A), sz_dn = align_up(D * F * 2, A);
+  const size_t per_layer = 2 * sz_norm + sz_qkv + sz_o + sz_gu + sz_dn;
+  const size_t sz_emb = align_up(V * D * 2, A);
+  const bool own_head = e->last && !(c.tie_embeddings && e->first);
+  size_t total = nl * per_layer + (e->first ? sz_emb : 0) + (e->last ? sz_norm : 0) + (own_head ? sz_emb : 0);
+  CK(cudaMalloc(&e->blob, total));
+  e->blob_bytes = total;
+  char* p = reinterpret_cast<char*>(e->blob);
+  auto take = [&](size_t n) { char* r = p; p += n; return reinterpret_cast<bf16*>(r); };
+  if (e->first) e->embed = take(sz_emb);
+  e->layers.resize(nl);
+  for (size_t li = 0; li < nl; ++li) {
+    LayerW& w = e->layers[li];
+    w.attn_norm = take(sz_norm); w.wqkv = take(sz_qkv); w.wo = take(sz_o);
+    w.mlp_norm = take(sz_norm); w.wgu = take(sz_gu); w.wdown = take(sz_dn);
+    const int l = start_layer + (int)li;
+    const std::string pre = "model.layers." + std::to_string(l) + ".";
+    const int t = l * 16;
+    auto add = [&](const char* nm, bf16* dst, int rows, int K, int mode, int stride, int off, int kind, float mean) {
+      e->slots[pre + nm] = TensorSlot{dst, rows, K, mode, stride, off, t + kind, 0.02f, mean, false};
+    };
+    add("input_layernorm.weight", w.attn_norm, 1, (int)D, 0, 1, 0, 0, 1.0f);
+    add("self_attn.q_proj.weight", w.wqkv, (int)(Hq * hd), (int)D, 1, 1, 0, 1, 0.f);
+    add("self_attn.k_proj.weight", w.wqkv, (int)(Hkv * hd), (int)D, 1, 1, (int)(Hq * hd), 2, 0.f);
+    add("self_attn.v_proj.weight", w.wqkv, (int)(Hkv * hd), (int)D, 0, 1, (int)((Hq + Hkv) * hd), 3, 0.f);
+    add("self_attn.o_proj.weight", w.wo, (int)D, (int)(Hq * hd), 0, 1, 0, 4, 0.f);
+    add("post_attention_layernorm.weight", w.mlp_norm, 1, (int)D, 0, 1, 0, 5, 1.0f);
+    add("mlp.gate_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 0, 6, 0.f);
+    add("mlp.up_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 1, 7, 0.f);
+    add("mlp.down_proj.weight", w.wdown, (int)D, (int)F, 0, 1, 0, 8, 0.f);
+  }
+  if (e->first)
+    e->slots["model.embed_tokens.weight"] = TensorSlot{e->embed, (int)V, (int)D, 0, 1, 0, (1 << 20), 0.02f, 0.f, false};
+  if (e->last) {
+    e->final_norm = take(sz_norm);
+    e->slots["model.norm.weight"] = TensorSlot{e->final_norm, 1, (int)D, 0, 1, 0, (1 << 20) + 1, 0.02f, 1.0f, false};
+    if (own_head) {
+      e->lm_head = take(sz_emb);
+      if (c.tie_embeddings)  // last-but-not-first shard of a tied model: the head IS the embedding table
+        e->slots["model.embed_tokens.weight"] = TensorSlot{e->lm_head, (int)V, (int)D, 0, 1, 0, (1 << 20), 0.02f, 0.f, false};
+      else
+        e->slots["lm_head.weight"] = TensorSlot{e->lm_head, (int)V, (int)D, 0, 1, 0, (1 << 20) + 2, 0.02f, 0.f, false};
+    } else {
+      e->lm_head = e->embed;
+    }
+  }
+  return 0;
+}
+
+int xotb200_load_tensor(xotb200_engine* e, const char* hf_name, const void* host_data, const int64_t* shape, int ndim) {
+  REQUIRE(e && hf_name && host_data && shape, "null argument");
+  REQUIRE(e->start >= 0, "no shard set");
+  CK(cudaSetDevice(e->device));
+  auto it = e->slots.find(hf_name);
+  if (it == e->slots.end()) return 1;  // not part of this shard
+  TensorSlot& s = it->second;
+  const int64_t rows = ndim == 2 ? shape[0] : 1, K = ndim == 2 ? shape[1] : shape[0];
+  REQUIRE((ndim == 1 || ndim == 2) && rows == s.rows && K == s.K, "tensor %s: shape mismatch (got %lld x %lld, want %d x %d)",
+          hf_name, (long long)rows, (long long)K, s.rows, s.K);
+  return upload_slot(e, s, host_data);
+}
+
+int xotb200_check_loaded(xotb200_engine* e) {
+  REQUIRE(e && e->start >= 0, "no shard set");
+  for (auto& kv : e->slots)
+    if (!kv.second.loaded) {
+      set_err("strict loader: tensor '%s' of shard [%d, %d] was never loaded", kv.first.c_str(), e->start, e->end);
+      return XOTB200_ESTRICT;
+    }
+  return 0;
+}
+
+int xotb200_load_shard(xotb200_engine* e, const char* dir, int start_layer, int end_layer) {
+  REQUIRE(e && dir, "null argument");
+  if (int rc = xotb200_set_shard(e, start_layer, end_layer)) return rc;
+  DIR* d = opendir(dir);
+  if (!d) { set_err("cannot open directory %s", dir); return XOTB200_EIO; }
+  std::vector<std::string> files;
+  while (struct dirent* de = readdir(d)) {
+    std::string n = de->d_name;
+    if (n.size() > 12 && n.substr(n.size() - 12) == ".safetensors") files.push_back(std::string(dir) + "/" + n);
+  }
+  closedir(d);
+  std::sort(files.begin(), files.end());
+  if (files.empty()) { set_err("no *.safetensors in %s", dir); return XOTB200_EIO; }
+  for (auto& f : files) {
+    int fd = open(f.c_str(), O_RDONLY);
+    if (fd < 0) { set_err("cannot open %s", f.c_str()); return XOTB200_EIO; }
+    struct stat sb;
+    fstat(fd, &sb);
+    void* m = mmap(nullptr, sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { set_err("mmap failed for %s", f.c_str()); return XOTB200_EIO; }
+    const char* base = static_cast<const char*>(m);
+    uint64_t hlen = 0;
+    memcpy(&hlen, base, 8);
+    std::map<std::string, StEntry> hdr;
+    int rc = 0;
+    if (hlen + 8 > (uint64_t)sb.st_size || !parse_st_header(base + 8, hlen, hdr)) {
+      set_err("bad safetensors header in %s", f.c_str());
+      rc = XOTB200_EIO;
+    }
+    for (auto it = hdr.begin(); rc == 0 && it != hdr.end(); ++it) {
+      auto sl = e->slots.find(it->first);
+      if (sl == e->slots.end()) continue;
+      const StEntry& en = it->second;
+      if (en.dtype != "BF16") { set_err("tensor %s: dtype %s unsupported (BF16 only)", it->first.c_str(), en.dtype.c_str()); rc = XOTB200_EIO; break; }
+      if ((uint64_t)(8 + hlen + en.end) > (uint64_t)sb.st_size) { set_err("tensor %s: data out of file bounds", it->first.c_str()); rc = XOTB200_EIO; break; }
+      rc = xotb200_load_tensor(e, it->first.c_str(), base + 8 + hlen + en.begin, en.shape.data(), (int)en.shape.size());
+      if (rc == 1) rc = 0;
+    }
+    munmap(m, sb.st_size);
+    if (rc) return rc;
+  }
+  return xotb200_check_loaded(e);
+}
+
+int xotb200_init_synthetic(xotb200_engine* e, uint64_t seed) {
+  REQUIRE(e && e->start >= 0, "no shard set");
+  CK(cudaSetDevice(e->device));
+  const double ih4_std = sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0);
+  for (auto& kv : e->slots) {
+    TensorSlot& s = kv.second;
+    const unsigned long long base = seed * 0x9E3779B97F4A7C15ull + (unsigned long long)s.tensor_id * 0xD1B54A32D192ED03ull;
+    const float scale = (float)((double)s.std / ih4_std);
+    synth_rows_kernel<<<s.rows, 256, 0, e->stream>>>(s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off, base, scale, s.mean);
+    CK(cudaGetLastError());
+    e->launches++;
+    s.loaded = true;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int xotb200_begin_request(xotb200_engine* e, int max_total_len) {
+  REQUIRE(e && e->start >= 0, "no shard set");
+  REQUIRE(max_total_len > 0 && max_total_len <= e->cfg.max_pos, "max_total_len %d out of range (max_position_embeddings %d)",
+          max_total_len, e->cfg.max_pos);
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const xotb200_model_cfg& c = e->cfg;
+  const size_t nl = e->end - e->start + 1;
+  if (max_total_len > e->L) {
+    if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
+    if (e->kv) { CK(cudaFree(e->kv)); e->kv = nullptr; }
+    e->L = max_total_len;
+    CK(cudaMalloc(&e->kv, nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim * 2));
+  }
+  if (max_total_len > e->rope_len) {
+    if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
+    // RoPE table: theta_j in fp32, angle = fp32(pos * theta_j), cos/sin correctly rounded
+    const int half = c.head_dim / 2;
+    std::vector<float> theta(half);
+    for (int j = 0; j < half; ++j) {
+      float ex = (float)(2 * j) / (float)c.head_dim;
+      float f = 1.0f / powf(c.rope_theta, ex);
+      if (c.rope_kind == XOTB200_ROPE_LLAMA3) {
+        const double low_wl = (double)c.rope_old_context_len / c.rope_low_freq_factor;
+        const double high_wl = (double)c.rope_old_context_len / c.rope_high_freq_factor;
+        const double wavelen = 2.0 * M_PI / (double)f;
+        if (wavelen < high_wl) {
+        } else if (wavelen > low_wl) {
+          f = f / c.rope_factor;
+        } else {
+          const double smooth = ((double)c.rope_old_context_len / wavelen - c.rope_low_freq_factor) /
+                                (c.rope_high_freq_factor - c.rope_low_freq_factor);
+          f = (float)((1.0 - smooth) * (double)f / c.rope_factor + smooth * (double)f);
+        }
+      }
+      theta[j] = f;
+    }
+    std::vector<float2> tab((size_t)max_total_len * half);
+    for (int p = 0; p < max_total_len; ++p)
+      for (int j = 0; j < half; ++j) {
+        const float ang = (float)p * theta[j];
+        tab[(size_t)p * half + j] = make_float2((float)cos((double)ang), (float)sin((double)ang));
+      }
+    if (e->rope) { CK(cudaFree(e->rope)); e->rope = nullptr; }
+    CK(cudaMalloc(&e->rope, tab.size() * sizeof(float2)));
+    CK(cudaMemcpy(e->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    e->rope_len = max_total_len;
+  }
+  // reset_caches (llm_utils.py:409-414): zero like torchtune's KVCache.reset
+  CK(cudaMemsetAsync(e->kv, 0, nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim * 2, e->stream));
+  CK(cudaMemsetAsync(e->ctl, 0, sizeof(StepCtl), e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->have_result = false;
+  return 0;
+}
+
+static int ensure_staging(xotb200_engine* e, int n) {
+  if (n <= e->stage_cap) return 0;
+  const size_t D = e->cfg.dim;
+  for (void* p : {(void*)e->stage_tokens, (void*)e->stage_f32, (void*)e->stage_in, (void*)e->stage_out})
+    if (p) cudaFree(p);
+  e->stage_tokens = nullptr; e->stage_f32 = nullptr; e->stage_in = e->stage_out = nullptr;
+  e->stage_cap = 0;
+  CK(cudaMalloc(&e->stage_tokens, (size_t)n * 4));
+  CK(cudaMalloc(&e->stage_f32, (size_t)n * D * 4));
+  CK(cudaMalloc(&e->stage_in, (size_t)n * D * 2));
+  CK(cudaMalloc(&e->stage_out, (size_t)n * D * 2));
+  e->stage_cap = n;
+  return 0;
+}
+
+int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidden_f32, int n_tokens, int pos0,
+                    float* out_f32) {
+  REQUIRE(e && e->start >= 0, "no shard set");
+  REQUIRE((tokens != nullptr) != (hidden_f32 != nullptr), "exactly one of tokens / hidden must be given");
+  REQUIRE((tokens != nullptr) == e->first, "%s shard expects %s", e->first ? "first" : "non-first",
+          e->first ? "token ids" : "a hidden state");
+  REQUIRE(n_tokens >= 1 && pos0 >= 0, "bad n_tokens/pos0");
+  REQUIRE(e->L > 0, "begin_request was not called");
+  REQUIRE(pos0 + n_tokens <= e->L, "KV cache overflow: pos0 %d + n %d > capacity %d", pos0, n_tokens, e->L);
+  REQUIRE(out_f32, "null output");
+  if (int rc = xotb200_check_loaded(e)) return rc;
+  CK(cudaSetDevice(e->device));
+  if (int rc = ensure_staging(e, n_tokens)) return rc;
+  const size_t D = e->cfg.dim;
+  cudaStream_t st = e->stream;
+  if (tokens) {
+    for (int i = 0; i < n_tokens; ++i)
+      REQUIRE(tokens[i] >= 0 && tokens[i] < e->cfg.vocab, "token id %d out of range", tokens[i]);
+    CK(cudaMemcpyAsync(e->stage_tokens, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    CK(cudaMemcpyAsync(e->stage_f32, hidden_f32, (size_t)n_tokens * D * 4, cudaMemcpyHostToDevice, st));
+    f32_to_bf16_kernel<<<256, 256, 0, st>>>(e->stage_f32, e->stage_in, (size_t)n_tokens * D);
+    CK(cudaGetLastError());
+    e->launches++;
+  }
+  for (int s = 0; s < n_tokens; ++s) {
+    if (int rc = launch_step(e, false, pos0 + s, s, s == n_tokens - 1, st)) return rc;
+    if (!e->last) CK(cudaMemcpyAsync(e->stage_out + (size_t)s * D, e->x, D * 2, cudaMemcpyDeviceToDevice, st));
+  }
+  if (e->last) {
+    CK(cudaMemcpyAsync(out_f32, e->logits, (size_t)e->cfg.vocab * 4, cudaMemcpyDeviceToHost, st));
+  } else {
+    bf16_to_f32_kernel<<<256, 256, 0, st>>>(e->stage_out, e->stage_f32, (size_t)n_tokens * D);
+    CK(cudaGetLastError());
+    e->launches++;
+    CK(cudaMemcpyAsync(out_f32, e->stage_f32, (size_t)n_tokens * D * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  e->have_result = true;
+  return 0;
+}
+
+int xotb200_last_token(xotb200_engine* e, int32_t* token) {
+  REQUIRE(e && token, "null argument");
+  REQUIRE(e->last && e->have_result, "no last-shard result available");
+  CK(cudaSetDevice(e->device));
+  StepCtl h;
+  CK(cudaMemcpy(&h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+  *token = h.token;
+  return 0;
+}
+
+int xotb200_inbox_export(xotb200_engine* e, void* out) {
+  REQUIRE(e && out, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == XOTB200_IPC_HANDLE_BYTES, "ipc handle size");
+  CK(cudaSetDevice(e->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->inbox));
+  memcpy(out, &h, sizeof(h));
+  return 0;
+}
+
+static void drop_next(xotb200_engine* e) {
+  if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
+  if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
+  e->next_inbox = nullptr;
+  e->next_ipc = false;
+}
+
+int xotb200_link_next_ipc(xotb200_engine* e, const void* handle) {
+  REQUIRE(e && handle, "null argument");
+  CK(cudaSetDevice(e->device));
+  drop_next(e);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  e->next_inbox = static_cast<InboxHdr*>(p);
+  e->next_ipc = true;
+  return 0;
+}
+
+int xotb200_link_next_local(xotb200_engine* e, xotb200_engine* next) {
+  REQUIRE(e && next, "null argument");
+  CK(cudaSetDevice(e->device));
+  drop_next(e);
+  if (next->device != e->device) {
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, e->device, next->device));
+    REQUIRE(can, "device %d cannot access peer %d", e->device, next->device);
+    cudaError_t er = cudaDeviceEnablePeerAccess(next->device, 0);
+    if (er != cudaSuccess && er != cudaErrorPeerAccessAlreadyEnabled) CK(er);
+    cudaGetLastError();
+  }
+  e->next_inbox = next->inbox;
+  return 0;
+}
+
+int xotb200_post_to_next(xotb200_engine* e, int step) {
+  REQUIRE(e && e->next_inbox, "next inbox not linked");
+  REQUIRE(e->have_result, "no forward result to post");
+  CK(cudaSetDevice(e->device));
+  if (e->last)
+    post_kernel<<<1, 256, 0, e->stream>>>(e->next_inbox, nullptr, e->cfg.dim, &e->ctl->token, step);
+  else
+    post_kernel<<<1, 256, 0, e->stream>>>(e->next_inbox, e->x, e->cfg.dim, nullptr, step);
+  CK(cudaGetLastError());
+  e->launches++;
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0) {
+  REQUIRE(e && e->start >= 0 && e->next_inbox, "ring not linked");
+  REQUIRE(n_steps >= 1 && n_steps <= MAX_RING_STEPS, "n_steps out of range (1..%d)", MAX_RING_STEPS);
+  REQUIRE(e->L > 0 && pos0 + n_steps <= e->L, "KV cache overflow: pos0 %d + steps %d > capacity %d", pos0, n_steps, e->L);
+  if (int rc = xotb200_check_loaded(e)) return rc;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  if (!e->ring_graph) {
+    cudaGraph_t g = nullptr;
+    const int64_t before = e->launches;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_step(e, true, 0, 0, true, st);
+    cudaError_t er = cudaStreamEndCapture(st, &g);
+    e->launches = before;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    CK(er);
+    er = cudaGraphInstantiate(&e->ring_graph, g, 0);
+    cudaGraphDestroy(g);
+    CK(er);
+  }
+  const int nl = e->end - e->start + 1;
+  const int per_step = 1 + 5 * nl + (e->last ? 1 : 0);
+  set_ctl_kernel<<<1, 1, 0, st>>>(e->ctl, pos0, step0, step0);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev0, st));
+  for (int i = 0; i < n_steps; ++i) CK(cudaGraphLaunch(e->ring_graph, st));
+  CK(cudaEventRecord(e->ev1, st));
+  e->launches += 1 + (int64_t)per_step * n_steps;
+  e->last_ring_steps = n_steps;
+  return 0;
+}
+
+int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float* ms_out) {
+  REQUIRE(e, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  StepCtl h;
+  CK(cudaMemcpy(&h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h.err) {
+    CK(cudaMemset(&e->ctl->err, 0, 4));
+    set_err("ring step %d: timed out waiting for the previous shard's flag", h.step);
+    return XOTB200_ETIMEOUT;
+  }
+  if (tokens_out) {
+    REQUIRE(e->last, "tokens are produced on the last shard");
+    REQUIRE(n_steps <= e->last_ring_steps, "n_steps exceeds the last ring run");
+    CK(cudaMemcpy(tokens_out, e->tokens_log, (size_t)n_steps * 4, cudaMemcpyDeviceToHost));
+  }
+  if (ms_out) CK(cudaEventElapsedTime(ms_out, e->ev0, e->ev1));
+  e->have_result = true;
+  return 0;
+}
+
+int xotb200_ring_timestamps(xotb200_engine* e, uint64_t* t_in, uint64_t* t_out, int n_steps) {
+  REQUIRE(e && t_in && t_out && n_steps <= MAX_RING_STEPS, "bad argument");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy(t_in, e->t_in, (size_t)n_steps * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(t_out, e->t_out, (size_t)n_steps * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int xotb200_kernel_launches(xotb200_engine* e, int64_t* count) {
+  REQUIRE(e && count, "null argument");
+  *count = e->launches;
+  return 0;
+}
+
+int xotb200_weight_bytes(xotb200_engine* e, int64_t* bytes) {
+  REQUIRE(e && bytes, "null argument");
+  *bytes = (int64_t)e->blob_bytes;
+  return 0;
+}
+
+int xotb200_step_bytes(xotb200_engine* e, int ctx, int64_t* bytes) {
+  REQUIRE(e && bytes && e->start >= 0, "bad argument");
+  const xotb200_model_cfg& c = e->cfg;
+  const int64_t D = c.dim, F = c.ffn, Hq = c.n_heads, Hkv = c.n_kv_heads, hd = c.head_dim, V = c.vocab;
+  const int64_t nl = e->end - e->start + 1;
+  int64_t b = nl * 2 * (D * Hq * hd + 2 * D * Hkv * hd + Hq * hd * D + 3 * D * F + 2 * D);
+  if (e->last) b += 2 * (V * D + D);
+  if (e->first) b += 2 * D;
+  b += 2 * 2 * Hkv * hd * nl * (int64_t)ctx + 2 * 2 * Hkv * hd * nl;
+  *bytes = b;
+  return 0;
+}
+
+}  // extern "C"

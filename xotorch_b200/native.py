@@ -1,0 +1,180 @@
+"""`NativeShard` — thin, synchronous Python owner of one `xotb200_engine*` (include/xotb200.h).  All compute is in
+libxotb200.so; this class only marshals numpy buffers and raises on error codes."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from pathlib import Path
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ModelCfg, check
+
+
+def cfg_from_hf(hf: dict) -> ModelCfg:
+  """HF config.json dict -> xotb200_model_cfg, following load_model_config
+  (/root/reference/xotorch/inference/llm_utils.py:79-126) with App. B2/B3 fixed (HF rope_scaling keys; unscaled RoPE
+  when rope_scaling is null)."""
+  dt = str(hf.get("torch_dtype", "bfloat16"))
+  if dt not in ("bfloat16", "bf16"):
+    raise ValueError(f"torch_dtype {dt!r}: libxotb200 implements bf16 weights only")
+  rs = hf.get("rope_scaling")
+  c = ModelCfg()
+  c.n_layers = hf["num_hidden_layers"]
+  c.dim = hf["hidden_size"]
+  c.ffn = hf["intermediate_size"]
+  c.n_heads = hf["num_attention_heads"]
+  c.n_kv_heads = hf["num_key_value_heads"]
+  c.head_dim = hf.get("head_dim") or hf["hidden_size"] // hf["num_attention_heads"]
+  c.vocab = hf["vocab_size"]
+  c.max_pos = int(hf["max_position_embeddings"])
+  c.rope_theta = float(hf.get("rope_theta", 10000.0))
+  c.norm_eps = float(hf["rms_norm_eps"])
+  c.tie_embeddings = 1 if hf.get("tie_word_embeddings", False) else 0
+  c.dtype = _lib.DTYPE_BF16
+  if rs is not None:
+    c.rope_kind = _lib.ROPE_LLAMA3
+    c.rope_factor = float(rs.get("factor", 32))
+    c.rope_low_freq_factor = float(rs.get("low_freq_factor", 1))
+    c.rope_high_freq_factor = float(rs.get("high_freq_factor", 4))
+    c.rope_old_context_len = int(rs.get("original_max_position_embeddings", 8192))
+  else:
+    c.rope_kind = _lib.ROPE_PLAIN
+    c.rope_factor, c.rope_low_freq_factor, c.rope_high_freq_factor, c.rope_old_context_len = 1.0, 1.0, 4.0, 8192
+  return c
+
+
+class NativeShard:
+  def __init__(self, hf_config: dict, device: int = 0):
+    self.lib = _lib.load()
+    self.hf_config = dict(hf_config)
+    self.cfg = cfg_from_hf(hf_config)
+    self.device = device
+    h = C.c_void_p()
+    check(self.lib.xotb200_create(C.byref(self.cfg), device, C.byref(h)))
+    self.h = h
+    self.start = self.end = -1
+
+  # -- lifetime ----------------------------------------------------------------------------------------------
+  def close(self):
+    if getattr(self, "h", None):
+      self.lib.xotb200_destroy(self.h)
+      self.h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  @property
+  def is_first(self) -> bool: return self.start == 0
+  @property
+  def is_last(self) -> bool: return self.end == self.cfg.n_layers - 1
+
+  # -- weights -----------------------------------------------------------------------------------------------
+  def load_dir(self, model_dir, start_layer: int, end_layer: int):
+    check(self.lib.xotb200_load_shard(self.h, str(model_dir).encode(), start_layer, end_layer))
+    self.start, self.end = start_layer, end_layer
+
+  def set_shard(self, start_layer: int, end_layer: int):
+    check(self.lib.xotb200_set_shard(self.h, start_layer, end_layer))
+    self.start, self.end = start_layer, end_layer
+
+  def init_synthetic(self, seed: int = 1234):
+    check(self.lib.xotb200_init_synthetic(self.h, C.c_uint64(seed)))
+
+  def load_tensor(self, hf_name: str, bf16_bits: np.ndarray) -> bool:
+    a = np.ascontiguousarray(bf16_bits)
+    assert a.dtype in (np.uint16, np.int16), "pass bf16 bit patterns (uint16)"
+    shp = (C.c_int64 * a.ndim)(*a.shape)
+    return check(self.lib.xotb200_load_tensor(self.h, hf_name.encode(), a.ctypes.data_as(C.c_void_p), shp, a.ndim)) == 0
+
+  def check_loaded(self):
+    check(self.lib.xotb200_check_loaded(self.h))
+
+  # -- request / step ----------------------------------------------------------------------------------------
+  def begin_request(self, max_total_len: int):
+    check(self.lib.xotb200_begin_request(self.h, int(max_total_len)))
+
+  def forward(self, input_data: np.ndarray, pos0: int) -> np.ndarray:
+    """ndim==2 int ids [1,S] (first shard) or ndim==3 float32 hidden [1,S,D] -> hidden [1,S,D] f32 or logits [1,V] f32."""
+    if input_data.ndim == 2:
+      ids = np.ascontiguousarray(input_data, dtype=np.int32)
+      n = ids.shape[1]
+      tok_p, hid_p = ids.ctypes.data_as(C.c_void_p), None
+    elif input_data.ndim == 3:
+      hid = np.ascontiguousarray(input_data, dtype=np.float32)
+      n = hid.shape[1]
+      tok_p, hid_p = None, hid.ctypes.data_as(C.c_void_p)
+    else:
+      raise ValueError(f"input_data.ndim must be 2 (token ids) or 3 (hidden state), got {input_data.ndim}")
+    if self.is_last:
+      out = np.empty((1, self.cfg.vocab), dtype=np.float32)
+    else:
+      out = np.empty((1, n, self.cfg.dim), dtype=np.float32)
+    check(self.lib.xotb200_forward(self.h, tok_p, hid_p, n, int(pos0), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+  def last_token(self) -> int:
+    t = C.c_int32()
+    check(self.lib.xotb200_last_token(self.h, C.byref(t)))
+    return int(t.value)
+
+  # -- ring ----------------------------------------------------------------------------------------------------
+  def inbox_export(self) -> bytes:
+    buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+    check(self.lib.xotb200_inbox_export(self.h, buf))
+    return buf.raw
+
+  def link_next_ipc(self, handle: bytes):
+    assert len(handle) == _lib.IPC_HANDLE_BYTES
+    check(self.lib.xotb200_link_next_ipc(self.h, C.create_string_buffer(handle, _lib.IPC_HANDLE_BYTES)))
+
+  def link_next_local(self, nxt: "NativeShard"):
+    check(self.lib.xotb200_link_next_local(self.h, nxt.h))
+
+  def post_to_next(self, step: int):
+    check(self.lib.xotb200_post_to_next(self.h, int(step)))
+
+  def ring_launch(self, n_steps: int, step0: int, pos0: int):
+    check(self.lib.xotb200_ring_launch(self.h, int(n_steps), int(step0), int(pos0)))
+
+  def ring_wait(self, n_steps: int = 0) -> Tuple[Optional[np.ndarray], float]:
+    ms = C.c_float()
+    toks = None
+    if self.is_last and n_steps > 0:
+      toks = np.empty(n_steps, dtype=np.int32)
+      check(self.lib.xotb200_ring_wait(self.h, toks.ctypes.data_as(C.c_void_p), n_steps, C.byref(ms)))
+    else:
+      check(self.lib.xotb200_ring_wait(self.h, None, 0, C.byref(ms)))
+    return toks, float(ms.value)
+
+  def ring_timestamps(self, n_steps: int) -> Tuple[np.ndarray, np.ndarray]:
+    t_in = np.empty(n_steps, dtype=np.uint64)
+    t_out = np.empty(n_steps, dtype=np.uint64)
+    check(self.lib.xotb200_ring_timestamps(self.h, t_in.ctypes.data_as(C.c_void_p), t_out.ctypes.data_as(C.c_void_p), n_steps))
+    return t_in, t_out
+
+  # -- introspection ---------------------------------------------------------------------------------------------
+  def kernel_launches(self) -> int:
+    v = C.c_int64()
+    check(self.lib.xotb200_kernel_launches(self.h, C.byref(v)))
+    return int(v.value)
+
+  def weight_bytes(self) -> int:
+    v = C.c_int64()
+    check(self.lib.xotb200_weight_bytes(self.h, C.byref(v)))
+    return int(v.value)
+
+  def step_bytes(self, ctx: int) -> int:
+    v = C.c_int64()
+    check(self.lib.xotb200_step_bytes(self.h, int(ctx), C.byref(v)))
+    return int(v.value)
+
+
+def load_hf_config(model_dir) -> dict:
+  with open(Path(model_dir) / "config.json", "r") as f:
+    return json.load(f)
