@@ -12,7 +12,7 @@ from xotorch_b200.synth import PRESETS, hf_config, synth_state_dict, synth_promp
 
 # Logit tolerance (bf16 model, fp32 accumulation, different summation order than the CPU oracle):
 # |delta| <= ATOL + RTOL*|logit|; bf16 has 8 significant bits (ulp = 2^-8 relative), a few ulps accumulate over depth.
-ATOL, RTOL = 0.02, 0.02
+ATOL, RTOL = 0.04, 0.02
 
 
 def _oracle(shape_name, shards, n_prompt, n_gen, force_ids=None, seed=1234):

@@ -272,6 +272,7 @@ static int launch_step(xotb200_engine* e, bool ring, int pos, int s, bool do_hea
     if (ring) {
       h.next_token = e->next_inbox->token;
       h.end.post_flag = e->next_inbox->flag_token;
+      h.end.post_step_offset = 1;
       h.end.advance = 1;
     }
     if (int rc = launch_gemv(e, PRO_NORM, EPI_HEAD, h, st)) return rc;

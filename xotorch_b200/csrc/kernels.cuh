@@ -147,6 +147,7 @@ struct StepEnd {
   unsigned int* ticket;        // device counter (library-owned), reset by the last CTA
   StepCtl* ctl;
   unsigned int* post_flag;     // base of the 2-entry flag array in the NEXT inbox (NULL: nothing to post)
+  int post_step_offset;        // 0: result feeds the SAME ring step of the next shard (hidden); 1: feeds step+1 (token)
   int advance;                 // 1: ring mode -> ctl->pos++, ctl->step++ and log timestamps
   unsigned long long* t_out;   // [MAX_RING_STEPS] log (ring mode)
 };
@@ -173,7 +174,8 @@ __device__ __forceinline__ void step_end_publish(const StepEnd& se) {  // thread
   }
   if (se.post_flag) {
     __threadfence_system();
-    st_release_sys(se.post_flag + (step & 1), (unsigned int)(step + 1));
+    const int ps = step + se.post_step_offset;
+    st_release_sys(se.post_flag + (ps & 1), (unsigned int)(ps + 1));
   }
   if (se.advance) {
     se.ctl->pos = se.ctl->pos + 1;
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
           const int li = step - a.ctl->run_step0;
           if (li >= 0 && li < MAX_RING_STEPS) a.tokens_out[li] = bi;
         }
-        if (a.next_token) a.next_token[step & 1] = bi;   // token slot of the first shard's inbox (peer store)
+        if (a.next_token) a.next_token[(step + 1) & 1] = bi;   // feeds ring step+1 of the first shard (peer store)
       }
       step_end_publish(a.end);
     }

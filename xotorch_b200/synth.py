@@ -94,7 +94,7 @@ _LLAMA32_SCALING = {"factor": 32.0, "high_freq_factor": 4.0, "low_freq_factor": 
 PRESETS: Dict[str, ModelShape] = {
   # tiny parity shapes (oracle runs in milliseconds)
   "tiny-llama-hd64": ModelShape("tiny-llama-hd64", 4, 512, 1536, 8, 2, 64, 2048, max_pos=2048),
-  "tiny-llama-hd128": ModelShape("tiny-llama-hd128", 3, 1024, 2816, 8, 2, 128, 4096, max_pos=2048),
+  "tiny-llama-hd128": ModelShape("tiny-llama-hd128", 3, 1024, 3072, 8, 2, 128, 4096, max_pos=2048),
   "tiny-llama-3.2": ModelShape("tiny-llama-3.2", 4, 512, 1536, 8, 2, 64, 2048, max_pos=4096, tie=True,
                                rope_scaling=dict(_LLAMA32_SCALING)),
   "llama-3.2-1b": ModelShape("llama-3.2-1b", 16, 2048, 8192, 32, 8, 64, 128256, max_pos=131072, tie=True,
