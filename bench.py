@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the shard-decode hot path.
+
+Metric (BASELINE.json): Llama-3-8B greedy decode tokens/sec (128-token prompt, 512 generated, batch 1) at N
+ring shards (one process per GPU, launched by torchrun for N>1), plus the mean inter-shard hop latency.
+
+A "step" is ONE request of the workload: a 128-token prefill (not timed, reported in `config`) followed by the timed
+512-token decode.  `value` = K*512 / (decode time of K requests): the device-resident ring (weights, KV and
+activations in HBM; on-device argmax feeds the next step; no host work per token), timed on the device with CUDA
+events on the launching stream, max over ranks.  `e2e` = the same metric through the host-buffer plugin API the
+reference's Node drives (`forward(ids/hidden ndarray) -> ndarray`, i.e. `InferenceEngine.infer_tensor`): every
+token copies its input host->device and its result (fp32 logits / hidden state) device->host inside the timed region.
+
+`python bench.py --impl reference` times the CPU restatement of the reference engine (oracle/, test infrastructure;
+the reference itself cannot be imported: torchtune is absent) on the host cores — a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_PROMPT, N_GEN = 128, 512
+MODEL = "llama-3-8b"
+SEED = 1234
+
+
+def _peaks():
+  p = ROOT / "MEASURED_PEAKS.json"
+  if p.exists():
+    try:
+      d = json.loads(p.read_text())
+      return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+      pass
+  return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+  """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index: int):
+    self.gpu, self.proc, self.lines = gpu_index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                    "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append((time.time(), line.strip()))
+
+  def stop(self, t0: float, t1: float) -> dict:
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    self.proc.terminate()
+    sm, mx, reasons = [], None, set()
+    for ts, ln in self.lines:
+      if ts < t0 or ts > t1 + 0.2:
+        continue
+      f = [x.strip() for x in ln.split(",")]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1])); mx = float(f[2])
+      except ValueError:
+        continue
+      for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        if v.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def usable_cores() -> int:
+  """Host cores this process may actually use: min(sched affinity, cgroup cpu quota) — os.cpu_count() reports the
+  whole host and oversubscribes a quota-limited container."""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+  for p in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+    try:
+      txt = Path(p).read_text().split()
+      if p.endswith("cpu.max"):
+        if txt[0] != "max":
+          n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+      else:
+        q = int(txt[0])
+        if q > 0:
+          per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+          n = min(n, max(1, int(q / per + 0.5)))
+      break
+    except Exception:
+      continue
+  return max(1, n)
+
+
+def even_partition(n_layers: int, n: int, rank: int):
+  """Ring partition for equal-memory GPUs == RingMemoryWeightedPartitioningStrategy + map_partitions_to_shards
+  (reference topology/*; xotorch_b200/topology/partitioning.py) on equal `memory`."""
+  from xotorch_b200.topology.partitioning import Partition, map_partitions_to_shards
+  parts, start = [], 0.0
+  for i in range(n):
+    end = round(start + 1.0 / n, 5)
+    parts.append(Partition(str(i), start, end))
+    start = end
+  shards = map_partitions_to_shards(parts, n_layers, MODEL)
+  return shards[rank].start_layer, shards[rank].end_layer
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (oracle = test infrastructure; only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(sample_layers: int = 2, decode_steps: int = 8, repeats: int = 1):
+  """Bounded sample of the SAME workload on the host cores: the 8B-shaped model cut to `sample_layers` layers + the
+  full embedding/lm_head rows it touches, 128-token prefill then `decode_steps` greedy steps; per-token time is
+  extrapolated to 32 layers (t_layer*32 + t_head).  Returns tokens/s and a description."""
+  import torch
+  from oracle.ref_engine import RefEngine, RefShard, model_config_from_hf
+  from oracle.synth_fast import synth_state_dict_fast
+  from xotorch_b200.synth import PRESETS, hf_config, synth_prompt
+  import dataclasses
+  shape = PRESETS[MODEL]
+  cores = usable_cores()
+  torch.set_num_threads(cores)
+  sd = synth_state_dict_fast(shape, SEED, layers=range(sample_layers))
+  prompt = synth_prompt(shape.vocab, N_PROMPT)
+
+  def run(n_layers):
+    sub = dataclasses.replace(shape, n_layers=n_layers)
+    cfg = model_config_from_hf(hf_config(sub))
+    eng = RefEngine(cfg, sd, RefShard(MODEL, 0, n_layers - 1, n_layers))
+    x, state = prompt.astype(np.int32), None
+    logits, state = eng.infer_tensor("cpu", eng.shard, x, state)           # prefill (untimed)
+    tok = eng.sample(logits, temp=0.0)
+    t0 = time.perf_counter()
+    for _ in range(decode_steps):
+      logits, state = eng.infer_tensor("cpu", eng.shard, tok.astype(np.int32).reshape(1, 1), state)
+      tok = eng.sample(logits, temp=0.0)                                   # reference sampler at temp 0 (node.py:121)
+    return (time.perf_counter() - t0) / decode_steps
+
+  best = None
+  for _ in range(repeats):
+    t_a = run(sample_layers)                 # sample_layers layers + head
+    t_b = run(max(1, sample_layers // 2))    # half the layers + head  -> separates per-layer from head cost
+    la, lb = sample_layers, max(1, sample_layers // 2)
+    t_layer = (t_a - t_b) / (la - lb) if la != lb else t_a / la
+    t_head = max(t_a - la * t_layer, 0.0)
+    t_tok = t_layer * shape.n_layers + t_head
+    best = t_tok if best is None else min(best, t_tok)
+  desc = (f"oracle RefEngine (bf16 CPU, full-L masked SDPA, GQA expand, reference sampler temp 0), {MODEL} shape cut to "
+          f"{sample_layers} and {max(1, sample_layers // 2)} layers + lm_head, 128-token prefill then {decode_steps} decode steps; "
+          f"per-token time extrapolated to {shape.n_layers} layers")
+  return 1.0 / best, cores, desc
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  t0 = time.time()
+  vals = []
+  for _ in range(max(1, min(args.steps, 2))):
+    v, cores, desc = cpu_reference_sample(sample_layers=2, decode_steps=8)
+    vals.append(v)
+  v = float(np.mean(vals))
+  line = {
+    "impl": "reference", "metric": "Llama-3-8B greedy decode tokens/sec (128-prompt/512-gen, batch 1)", "value": round(v, 4),
+    "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    "ms_per_step": round(N_GEN / v * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    "dtype": "bf16", "data": "synthetic",
+    "config": {"workload": f"{MODEL} shape, synthetic bf16 weights (seed {SEED}), {N_PROMPT}-token prompt / {N_GEN} generated, batch 1, CPU",
+               "shards": args.gpus},
+    "cpu_baseline": {"value": round(v, 4), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
+    "e2e": {"value": round(v, 4), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "wall_s": round(time.time() - t0, 1),
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  from xotorch_b200.native import NativeShard
+  from xotorch_b200.synth import PRESETS, hf_config, synth_prompt
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+  n = world
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py: no CUDA device — xotorch_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+  torch.cuda.set_device(local)
+  if n > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+  shape = PRESETS[MODEL]
+  cfg = hf_config(shape)
+  a, b = even_partition(shape.n_layers, n, rank) if n > 1 else (0, shape.n_layers - 1)
+  eng = NativeShard(cfg, device=local)
+  eng.set_shard(a, b)
+  eng.init_synthetic(SEED)
+  first, last = eng.is_first, eng.is_last
+  prev_r, next_r = (rank - 1) % n, (rank + 1) % n
+  D, V = shape.dim, shape.vocab
+
+  # ---- link the ring: every engine learns the inbox of the next one (CUDA IPC across processes) ----
+  if n == 1:
+    eng.link_next_local(eng)
+  else:
+    handles = [None] * n
+    dist.all_gather_object(handles, eng.inbox_export())
+    eng.link_next_ipc(handles[next_r])
+    dist.barrier()
+
+  prompt = synth_prompt(V, N_PROMPT)
+  max_len = N_PROMPT + N_GEN + 1
+  dev = torch.device("cuda", local)
+
+  def hop_send(arr: np.ndarray):          # prefill / API-path hop: host ndarray -> next rank (NCCL send of the fp32 payload)
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev)
+    dist.send(t, next_r)
+
+  def hop_recv(shape_):
+    t = torch.empty(shape_, dtype=torch.float32, device=dev)
+    dist.recv(t, prev_r)
+    return t.cpu().numpy()
+
+  def prefill():
+    """128-token prefill through the host-buffer API; hidden state handed over per shard (bytes = 2*S*D algorithmic)."""
+    eng.begin_request(max_len)
+    if n == 1:
+      return eng.forward(prompt, 0)
+    if first:
+      h = eng.forward(prompt, 0); hop_send(h); return None
+    h = hop_recv((1, N_PROMPT, D))
+    out = eng.forward(h, 0)
+    if not last:
+      hop_send(out); return None
+    return out
+
+  step_ctr = [0]
+
+  def ring_decode(n_steps: int):
+    """device-resident ring: last shard seeds shard 0 with the first generated token, then n_steps graph replays/rank."""
+    s0 = step_ctr[0]
+    if last:
+      eng.post_to_next(s0)
+    if n > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    eng.ring_launch(n_steps, s0, N_PROMPT)
+    toks, ms = eng.ring_wait(n_steps)
+    step_ctr[0] += n_steps
+    return toks, ms
+
+  def barrier():
+    if n > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(v: float) -> float:
+    if n == 1:
+      return v
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  # ---- warm-up requests ----
+  prefill_ms = None
+  for _ in range(max(args.warmup, 0)):
+    t0 = time.perf_counter(); prefill(); barrier(); prefill_ms = (time.perf_counter() - t0) * 1e3
+    ring_decode(N_GEN)
+  # ---- timed: K requests, decode phases timed with CUDA events on the launching stream ----
+  sampler = ClockSampler(local)
+  launches0 = eng.kernel_launches()
+  dec_ms, ring_tokens, hop_stats = [], None, []
+  t_region0 = time.time()
+  sampler.start()
+  barrier()
+  for k in range(args.steps):
+    t0 = time.perf_counter(); prefill(); barrier(); prefill_ms = (time.perf_counter() - t0) * 1e3
+    l0 = eng.kernel_launches()
+    toks, ms = ring_decode(N_GEN)
+    dec_ms.append(max_over_ranks(ms))
+    launches_decode = eng.kernel_launches() - l0
+    if toks is not None:
+      ring_tokens = toks
+    # hop accounting: per-step compute span on each rank (own clock) vs ring period on rank 0
+    t_in, t_out = eng.ring_timestamps(N_GEN)
+    comp = (t_out.astype(np.int64) - t_in.astype(np.int64)).astype(np.float64)     # ns, per step, this shard
+    if n > 1:
+      allc = [None] * n
+      dist.all_gather_object(allc, comp)
+      period = np.diff(t_in.astype(np.int64)).astype(np.float64)                   # rank-local ring period
+      if rank == 0:
+        tot = np.sum(np.stack(allc), axis=0)[:-1]
+        hop_stats.append((period - tot) / n)                                       # mean per-hop ns in each ring turn
+  barrier()
+  t_region1 = time.time()
+  clocks = sampler.stop(t_region0, t_region1)
+  total_ms = float(np.sum(dec_ms))
+  value = args.steps * N_GEN / (total_ms * 1e-3)
+  gpu_launches = (eng.kernel_launches() - launches0)
+
+  # ---- e2e: host-buffer API per token (H2D ids/hidden in, D2H logits/hidden out, every step) ----
+  def api_request():
+    prefill_out = prefill()
+    pos = N_PROMPT
+    tok = int(np.argmax(prefill_out[0])) if last else 0
+    if n > 1:
+      tt = torch.tensor([tok], dtype=torch.int64, device=dev)
+      dist.broadcast(tt, n - 1)
+      tok = int(tt.item())
+    barrier()
+    t0 = time.perf_counter()
+    out_ids = []
+    for i in range(N_GEN):
+      if n == 1:
+        logits = eng.forward(np.array([[tok]], dtype=np.int32), pos)
+        tok = int(np.argmax(logits[0]))
+      else:
+        if first:
+          h = eng.forward(np.array([[tok]], dtype=np.int32), pos)
+          hop_send(h)
+        else:
+          h = hop_recv((1, 1, D))
+          o = eng.forward(h, pos)
+          if not last:
+            hop_send(o)
+          else:
+            tok = int(np.argmax(o[0]))
+        tt = torch.tensor([tok], dtype=torch.int64, device=dev)
+        dist.broadcast(tt, n - 1)               # ring closure: token id back to shard 0 (4-byte payload)
+        tok = int(tt.item())
+      out_ids.append(tok)
+      pos += 1
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0), out_ids
+
+  api_request()                                 # warm
+  e2e_times, e2e_ids = [], None
+  for _ in range(max(1, min(args.steps, 2))):
+    dt, e2e_ids = api_request()
+    e2e_times.append(max_over_ranks(dt))
+  e2e_value = N_GEN / float(np.mean(e2e_times))
+  h2d = (N_PROMPT * 4 + N_GEN * 4) if first else (N_PROMPT * D * 4 + N_GEN * D * 4)
+  d2h = ((N_GEN + 1) * V * 4) if last else (N_PROMPT * D * 4 + N_GEN * D * 4)
+
+  # ---- roofline of the decode step (algorithmic bytes of SURVEY.md §8d / DESIGN.md, live CUDA-event time) ----
+  peak, peak_src = _peaks()
+  ctx_avg = N_PROMPT + (N_GEN - 1) / 2.0
+  step_bytes_local = eng.step_bytes(int(round(ctx_avg)))
+  if n > 1:
+    allb = [None] * n
+    dist.all_gather_object(allb, step_bytes_local)
+    step_bytes_total = int(sum(allb))
+  else:
+    step_bytes_total = step_bytes_local
+  achieved = step_bytes_total * args.steps * N_GEN / (total_ms * 1e-3) / 1e9
+
+  ids_match_api = bool(ring_tokens is not None and e2e_ids is not None and list(ring_tokens[:N_GEN - 1]) == e2e_ids[:N_GEN - 1]) if n == 1 else None
+
+  if rank == 0 or (n > 1 and last):
+    pass
+  # gather the last rank's knowledge on rank 0
+  if n > 1:
+    info = [None] * n
+    dist.all_gather_object(info, {"ring_tokens": None if ring_tokens is None else ring_tokens[:8].tolist()})
+    first_ids = [x["ring_tokens"] for x in info if x["ring_tokens"] is not None][0]
+  else:
+    first_ids = ring_tokens[:8].tolist()
+
+  if rank == 0:
+    cpu = None
+    if n == 1 and not args.no_cpu_baseline:
+      try:
+        v, cores, desc = cpu_reference_sample(sample_layers=2, decode_steps=8)
+        cpu = {"value": round(v, 4), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc}
+      except Exception as ex:  # the CPU leg must never take the GPU number down with it
+        cpu = {"value": None, "unit": "tokens/s", "cores": usable_cores(), "kind": "port", "sample": f"failed: {ex!r}"}
+    hop = None
+    if hop_stats:
+      hs = np.concatenate(hop_stats) / 1e3
+      hop = {"p50_us": round(float(np.median(hs)), 2), "p90_us": round(float(np.percentile(hs, 90)), 2),
+             "how": "per ring turn: (rank-0 ring period - sum over shards of [flag observed -> result posted], each on its own globaltimer) / n_hops"}
+    line = {
+      "metric": "Llama-3-8B greedy decode tokens/sec (128-prompt/512-gen, batch 1)", "value": round(value, 2), "unit": "tokens/s",
+      "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 3),
+      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+      "config": {"workload": f"{MODEL} shape, synthetic bf16 weights (seed {SEED}, device-generated), {N_PROMPT}-token prompt / "
+                             f"{N_GEN} generated, batch 1, greedy; step = one request, decode phase timed",
+                 "shards": n, "layers_per_shard": (b - a + 1), "partitioning": "ring, equal HBM",
+                 "l2_policy": "inputs larger than L2 (15 GB of weights streamed per token vs 126 MB L2)",
+                 "prefill_ms_host_api": round(prefill_ms, 1), "first_ids": first_ids,
+                 "ring_ids_equal_api_ids": ids_match_api},
+      "clocks": clocks, "gpu_launches": int(gpu_launches),
+      "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+              "how": "NativeShard.forward (== InferenceEngine.infer_tensor) per token with host ndarrays; host argmax; "
+                     + ("NCCL send/recv of the fp32 hidden state between ranks" if n > 1 else "single shard")},
+      "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                   "traffic": None, "peak_source": peak_src,
+                   "kernel": "whole decode step (all shard kernels of one token), algorithmic bytes = weights once + valid KV",
+                   "bytes_per_token": step_bytes_total},
+      "hop": hop, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+  if n > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=3)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,38 @@
+"""TEST INFRASTRUCTURE: ctypes wrapper around oracle/synth_fast.c (falls back to the torch generator if gcc output
+is unavailable).  Produces the same tensors as xotorch_b200.synth.synth_state_dict, much faster."""
+import ctypes as C
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from xotorch_b200 import synth
+from .build import build, OUT
+
+_lib = None
+
+
+def _load():
+  global _lib
+  if _lib is None:
+    lib = C.CDLL(str(build()))
+    lib.synth_fill_bf16.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float]
+    lib.synth_fill_bf16.restype = None
+    _lib = lib
+  return _lib
+
+
+def synth_tensor_fast(seed: int, tensor_id: int, shape, std: float, mean: float) -> torch.Tensor:
+  n = int(np.prod(shape))
+  out = torch.empty(n, dtype=torch.bfloat16)
+  scale = np.float32(std / synth.IH4_STD)
+  _load().synth_fill_bf16(C.c_void_p(out.data_ptr()), C.c_uint64(synth.tensor_base(seed, tensor_id)), 0, n,
+                          C.c_float(float(scale)), C.c_float(mean))
+  return out.view(*shape)
+
+
+def synth_state_dict_fast(shape: synth.ModelShape, seed: int = 1234, layers: Optional[Iterable[int]] = None,
+                          with_embed: bool = True, with_head: bool = True) -> Dict[str, torch.Tensor]:
+  assert shape.dtype == "bfloat16"
+  return {name: synth_tensor_fast(seed, tid, shp, std, mean)
+          for name, tid, shp, std, mean in synth.hf_tensor_specs(shape, layers, with_embed, with_head)}
