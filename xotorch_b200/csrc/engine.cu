@@ -27,6 +27,7 @@
 
 #include "../../include/xotb200.h"
 #include "kernels.cuh"
+#include "megakernel.cuh"
 
 using namespace xb;
 
@@ -68,11 +69,6 @@ struct LayerW {
   bf16 *attn_norm, *wqkv, *wo, *mlp_norm, *wgu, *wdown;
 };
 
-struct GemvCfg {
-  int tr, tk, stages;
-  size_t smem;
-};
-
 struct xotb200_engine {
   xotb200_model_cfg cfg;
   int device = 0, sm_count = 148;
@@ -109,7 +105,11 @@ struct xotb200_engine {
   bf16 *stage_in = nullptr, *stage_out = nullptr;
   bool have_result = false;
   cudaStream_t stream = nullptr;
-  cudaGraphExec_t ring_graph = nullptr;
+  LayerDev* d_layers = nullptr;
+  unsigned int* bar_counter = nullptr;
+  void* mega = nullptr;
+  size_t mega_smem = 0;
+  int mega_xbuf = 0, mega_grid = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   int last_ring_steps = 0;
@@ -118,165 +118,77 @@ struct xotb200_engine {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // --------------------------------------------------------------------------------------------------------------
-// kernel dispatch
+// megakernel dispatch
 // --------------------------------------------------------------------------------------------------------------
-typedef void (*gemv_fn)(const GemvArgs);
+typedef void (*mega_fn)(const MegaArgs);
 
-template <int PRO, int EPI>
-static gemv_fn pick_gemv(int tr, int tk) {
-  if (tr == 2 && tk == 2048) return gemv_kernel<2, 2048, PRO, EPI>;
-  if (tr == 4 && tk == 1024) return gemv_kernel<4, 1024, PRO, EPI>;
-  if (tr == 2 && tk == 1024) return gemv_kernel<2, 1024, PRO, EPI>;
-  if (tr == 4 && tk == 512) return gemv_kernel<4, 512, PRO, EPI>;
-  if (tr == 2 && tk == 512) return gemv_kernel<2, 512, PRO, EPI>;
-  return nullptr;
+template <int TK, int HD>
+static mega_fn pick_mega_r(int R) {
+  switch (R) {
+    case 2: return shard_step_kernel<TK, HD, 2>;
+    case 4: return shard_step_kernel<TK, HD, 4>;
+    case 8: return shard_step_kernel<TK, HD, 8>;
+    default: return nullptr;
+  }
 }
-static gemv_fn pick_gemv_dyn(int pro, int epi, int tr, int tk) {
-  if (pro == PRO_NORM && epi == EPI_QKV) return pick_gemv<PRO_NORM, EPI_QKV>(tr, tk);
-  if (pro == PRO_PLAIN && epi == EPI_RESID) return pick_gemv<PRO_PLAIN, EPI_RESID>(tr, tk);
-  if (pro == PRO_NORM && epi == EPI_SWIGLU) return pick_gemv<PRO_NORM, EPI_SWIGLU>(tr, tk);
-  if (pro == PRO_NORM && epi == EPI_HEAD) return pick_gemv<PRO_NORM, EPI_HEAD>(tr, tk);
+static mega_fn pick_mega(int tk, int hd, int R) {
+  if (tk == 2048 && hd == 128) return pick_mega_r<2048, 128>(R);
+  if (tk == 2048 && hd == 64) return pick_mega_r<2048, 64>(R);
+  if (tk == 512 && hd == 128) return pick_mega_r<512, 128>(R);
+  if (tk == 512 && hd == 64) return pick_mega_r<512, 64>(R);
   return nullptr;
 }
 
 static const size_t SMEM_BUDGET = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
 
-// Choose the tile shape for an [N, K] GEMV on `grid` CTAs: K-chunk = largest of {2048,1024,512} dividing K,
-// rows-per-tile in {2,4} minimising the row imbalance across CTAs (8 KiB stages preferred).
-static GemvCfg choose_gemv(int N, int K, int grid, bool need_pairs) {
-  GemvCfg best{};
-  double best_score = -1;
-  const int cands[5][2] = {{4, 1024}, {2, 2048}, {2, 1024}, {4, 512}, {2, 512}};
-  for (auto& c : cands) {
-    const int tr = c[0], tk = c[1];
-    if (K % tk != 0 || N % tr != 0) continue;
-    (void)need_pairs;
-    const int groups = N / tr;
-    const int maxg = (groups + grid - 1) / grid;
-    double eff = (double)groups / ((double)grid * maxg);
-    const size_t stage = (size_t)tr * tk * 2;
-    const size_t fixed = (size_t)K * 2 + 1024;
-    int stages = (int)((SMEM_BUDGET - fixed) / (NW * stage));
-    if (stages < 2) continue;
-    if (stages > 8) stages = 8;
-    // prefer larger copies / fewer x re-reads on near ties
-    double score = eff + 1e-3 * (tk / 2048.0) + 5e-4 * (tr / 4.0);
-    if (score > best_score) {
-      best_score = score;
-      best.tr = tr;
-      best.tk = tk;
-      best.stages = stages;
-      best.smem = (size_t)NW * stages * stage + (size_t)K * 2 + (size_t)NW * stages * 8 + 128;
-    }
-  }
-  return best;
-}
-
-static int launch_gemv(xotb200_engine* e, int pro, int epi, GemvArgs& a, cudaStream_t st) {
-  const int grid = std::min(e->sm_count, a.N / 2);
-  GemvCfg c = choose_gemv(a.N, a.K, grid, true);
-  REQUIRE(c.tr != 0, "no GEMV tile shape for N=%d K=%d (K must be a multiple of 512, N of 2)", a.N, a.K);
-  gemv_fn fn = pick_gemv_dyn(pro, epi, c.tr, c.tk);
-  REQUIRE(fn != nullptr, "no GEMV instantiation pro=%d epi=%d tr=%d tk=%d", pro, epi, c.tr, c.tk);
-  a.stages = c.stages;
-  {
-    static std::map<std::pair<int, void*>, size_t> attr_done;   // (device, kernel) -> opted-in smem
-    auto key = std::make_pair(e->device, (void*)fn);
-    auto it = attr_done.find(key);
-    if (it == attr_done.end() || it->second < c.smem) {
-      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-      attr_done[key] = c.smem;
-    }
-  }
-  fn<<<grid, GEMV_THREADS, c.smem, st>>>(a);
-  CK(cudaGetLastError());
-  e->launches++;
-  return 0;
-}
-
-template <int HD>
-static int launch_attn_hd(xotb200_engine* e, const AttnArgs& a, int R, cudaStream_t st) {
-  dim3 grid(e->nsplit, e->cfg.n_kv_heads);
-  switch (R) {
-    case 1: attn_decode_kernel<HD, 1><<<grid, 128, 0, st>>>(a); break;
-    case 2: attn_decode_kernel<HD, 2><<<grid, 128, 0, st>>>(a); break;
-    case 4: attn_decode_kernel<HD, 4><<<grid, 128, 0, st>>>(a); break;
-    case 8: attn_decode_kernel<HD, 8><<<grid, 128, 0, st>>>(a); break;
-    default: set_err("unsupported GQA ratio %d", R); return XOTB200_EINVAL;
-  }
-  CK(cudaGetLastError());
-  e->launches++;
-  return 0;
-}
-
-// One step of the shard.  ring: inputs from the inbox / outputs to the next inbox, position from ctl.
-// direct: position given, input row `s` of the staging buffers; `do_head` only on the last shard.
-static int launch_step(xotb200_engine* e, bool ring, int pos, int s, bool do_head, cudaStream_t st) {
+// Resolve the kernel instantiation, shared-memory size and grid for this engine (once per engine).
+static int prepare_mega(xotb200_engine* e) {
+  if (e->mega) return 0;
   const xotb200_model_cfg& c = e->cfg;
-  const int D = c.dim, F = c.ffn, Hq = c.n_heads, Hkv = c.n_kv_heads, hd = c.head_dim;
-  const int nl = e->end - e->start + 1;
-  {
-    IngestArgs ia{};
-    ia.ctl = e->ctl; ia.inbox = e->inbox; ia.embed = e->first ? e->embed : nullptr; ia.x = e->x; ia.D = D;
-    ia.direct = ring ? 0 : 1; ia.pos = pos;
-    ia.src_token = (!ring && e->first) ? e->stage_tokens + s : nullptr;
-    ia.src_hidden = (!ring && !e->first) ? e->stage_in + (size_t)s * D : nullptr;
-    ia.t_in = e->t_in;
-    ingest_kernel<<<1, 256, 0, st>>>(ia);
-    CK(cudaGetLastError());
-    e->launches++;
-  }
-  for (int li = 0; li < nl; ++li) {
-    const LayerW& w = e->layers[li];
-    bf16* kc = e->kv + ((size_t)li * 2 + 0) * Hkv * e->L * hd;
-    bf16* vc = e->kv + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
-    GemvArgs a{};
-    // qkv
-    a.W = w.wqkv; a.N = (Hq + 2 * Hkv) * hd; a.K = D; a.x_in = e->x; a.norm_w = w.attn_norm; a.eps = c.norm_eps;
-    a.ctl = e->ctl; a.q_out = e->q; a.k_cache = kc; a.v_cache = vc; a.rope = e->rope; a.q_rows = Hq * hd;
-    a.kv_rows = Hkv * hd; a.hd = hd; a.L = e->L;
-    if (int rc = launch_gemv(e, PRO_NORM, EPI_QKV, a, st)) return rc;
-    // attention
-    AttnArgs aa{};
-    aa.q = e->q; aa.k_cache = kc; aa.v_cache = vc; aa.out = e->attn_out; aa.part_ml = e->part_ml;
-    aa.part_acc = e->part_acc; aa.tickets = e->tickets; aa.ctl = e->ctl; aa.L = e->L;
-    aa.scale = 1.0f / sqrtf((float)hd);
-    int rc = hd == 128 ? launch_attn_hd<128>(e, aa, Hq / Hkv, st) : launch_attn_hd<64>(e, aa, Hq / Hkv, st);
-    if (rc) return rc;
-    // o-proj + residual
-    GemvArgs o{};
-    o.W = w.wo; o.N = D; o.K = Hq * hd; o.x_in = e->attn_out; o.ctl = e->ctl; o.res = e->x; o.out = e->x;
-    if ((rc = launch_gemv(e, PRO_PLAIN, EPI_RESID, o, st))) return rc;
-    // gate/up + SwiGLU
-    GemvArgs g{};
-    g.W = w.wgu; g.N = 2 * F; g.K = D; g.x_in = e->x; g.norm_w = w.mlp_norm; g.eps = c.norm_eps; g.ctl = e->ctl;
-    g.out = e->act;
-    if ((rc = launch_gemv(e, PRO_NORM, EPI_SWIGLU, g, st))) return rc;
-    // down + residual (last layer of a non-last shard in ring mode: also store to the next inbox + release flag)
-    GemvArgs d{};
-    d.W = w.wdown; d.N = D; d.K = F; d.x_in = e->act; d.ctl = e->ctl; d.res = e->x; d.out = e->x;
-    if (ring && li == nl - 1 && !e->last) {
-      d.out_peer = reinterpret_cast<bf16*>(reinterpret_cast<char*>(e->next_inbox) + sizeof(InboxHdr));
-      d.final_kernel = 1;
-      d.end.ticket = e->tickets + Hkv; d.end.ctl = e->ctl; d.end.post_flag = e->next_inbox->flag_hidden;
-      d.end.advance = 1; d.end.t_out = e->t_out;
-    }
-    if ((rc = launch_gemv(e, PRO_PLAIN, EPI_RESID, d, st))) return rc;
-  }
-  if (e->last && (ring || do_head)) {
-    GemvArgs h{};
-    h.W = e->lm_head; h.N = c.vocab; h.K = D; h.x_in = e->x; h.norm_w = e->final_norm; h.eps = c.norm_eps;
-    h.ctl = e->ctl; h.logits = e->logits; h.cta_best_val = e->cta_best_val; h.cta_best_idx = e->cta_best_idx;
-    h.tokens_out = e->tokens_log; h.final_kernel = 1;
-    h.end.ticket = e->tickets + Hkv; h.end.ctl = e->ctl; h.end.t_out = e->t_out;
-    if (ring) {
-      h.next_token = e->next_inbox->token;
-      h.end.post_flag = e->next_inbox->flag_token;
-      h.end.post_step_offset = 1;
-      h.end.advance = 1;
-    }
-    if (int rc = launch_gemv(e, PRO_NORM, EPI_HEAD, h, st)) return rc;
-  }
+  const int qdim = c.n_heads * c.head_dim;
+  const int tk = (c.dim % 2048 == 0 && c.ffn % 2048 == 0 && qdim % 2048 == 0) ? 2048 : 512;
+  const int R = c.n_heads / c.n_kv_heads;
+  mega_fn fn = pick_mega(tk, c.head_dim, R);
+  REQUIRE(fn != nullptr, "no megakernel instantiation for tk=%d head_dim=%d gqa=%d", tk, c.head_dim, R);
+  const size_t kmax = (size_t)std::max(std::max(c.dim, c.ffn), qdim);
+  const size_t attn_scratch = ((size_t)NW * R * 2 + (size_t)NW * R * c.head_dim) * 4;
+  const size_t xbuf = align_up(std::max(kmax * 2, attn_scratch), 128);
+  const size_t smem = (size_t)NW * MK_S * MK_TR * tk * 2 + xbuf + (size_t)NW * MK_S * 8 + 256;
+  REQUIRE(smem <= SMEM_BUDGET, "shared memory %zu > %zu: activation width %zu too large for the ring", smem, SMEM_BUDGET, kmax);
+  CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, GEMV_THREADS, smem));
+  REQUIRE(per_sm >= 1, "megakernel does not fit on an SM");
+  e->mega = (void*)fn;
+  e->mega_smem = smem;
+  e->mega_xbuf = (int)xbuf;
+  e->mega_grid = e->sm_count;   // one CTA per SM, all co-resident (cooperative launch checks it)
+  return 0;
+}
+
+// Launch the persistent shard-step kernel for n_steps steps.  mode 0 = ring (inbox in, next inbox out),
+// mode 1 = direct (staging buffers).
+static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int pos0, cudaStream_t st) {
+  if (int rc = prepare_mega(e)) return rc;
+  const xotb200_model_cfg& c = e->cfg;
+  MegaArgs a{};
+  a.layers = e->d_layers; a.nl = e->end - e->start + 1;
+  a.D = c.dim; a.F = c.ffn; a.Hq = c.n_heads; a.Hkv = c.n_kv_heads; a.hd = c.head_dim; a.V = c.vocab; a.L = e->L;
+  a.eps = c.norm_eps; a.attn_scale = 1.0f / sqrtf((float)c.head_dim); a.rope = e->rope;
+  a.embed = e->embed; a.final_norm = e->final_norm; a.lm_head = e->lm_head;
+  a.first = e->first ? 1 : 0; a.last = e->last ? 1 : 0;
+  a.x = e->x; a.q = e->q; a.attn_out = e->attn_out; a.act = e->act; a.logits = e->logits;
+  a.part_ml = e->part_ml; a.part_acc = e->part_acc; a.tickets = e->tickets;
+  a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit;
+  a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
+  a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
+  a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
+  a.src_tokens = e->stage_tokens; a.src_hidden = e->stage_in; a.out_hidden = e->stage_out;
+  a.xbuf_bytes = e->mega_xbuf;
+  CK(cudaMemsetAsync(e->bar_counter, 0, 4, st));
+  void* params[] = {&a};
+  CK(cudaLaunchCooperativeKernel((const void*)e->mega, dim3(e->mega_grid), dim3(GEMV_THREADS), params, e->mega_smem, st));
+  e->launches++;
   return 0;
 }
 
@@ -356,7 +268,7 @@ static bool parse_st_header(const char* s, size_t n, std::map<std::string, StEnt
 // helpers
 // --------------------------------------------------------------------------------------------------------------
 static void free_shard(xotb200_engine* e) {
-  if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
+  if (e->d_layers) { cudaFree(e->d_layers); e->d_layers = nullptr; }
   if (e->blob) { cudaFree(e->blob); e->blob = nullptr; }
   if (e->kv) { cudaFree(e->kv); e->kv = nullptr; }
   e->layers.clear();
@@ -434,6 +346,7 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   CK(cudaMemset(e->tickets, 0, (Hkv + 1) * 4));
   CK(cudaMalloc(&e->cta_best_val, 1024 * 4));
   CK(cudaMalloc(&e->cta_best_idx, 1024 * 4));
+  CK(cudaMalloc(&e->bar_counter, 4));
   CK(cudaMalloc(&e->ctl, sizeof(StepCtl)));
   CK(cudaMemset(e->ctl, 0, sizeof(StepCtl)));
   const size_t inbox_bytes = sizeof(InboxHdr) + (size_t)2 * D * 2;
@@ -455,7 +368,7 @@ int xotb200_destroy(xotb200_engine* e) {
   free_shard(e);
   if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
   void* ptrs[] = {e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
-                  e->cta_best_idx, e->ctl, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
+                  e->cta_best_idx, e->ctl, e->bar_counter, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
                   e->stage_f32, e->stage_in, e->stage_out};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -625,13 +538,11 @@ int xotb200_begin_request(xotb200_engine* e, int max_total_len) {
   const xotb200_model_cfg& c = e->cfg;
   const size_t nl = e->end - e->start + 1;
   if (max_total_len > e->L) {
-    if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
     if (e->kv) { CK(cudaFree(e->kv)); e->kv = nullptr; }
     e->L = max_total_len;
     CK(cudaMalloc(&e->kv, nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim * 2));
   }
   if (max_total_len > e->rope_len) {
-    if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
     // RoPE table: theta_j in fp32, angle = fp32(pos * theta_j), cos/sin correctly rounded
     const int half = c.head_dim / 2;
     std::vector<float> theta(half);
@@ -663,6 +574,17 @@ int xotb200_begin_request(xotb200_engine* e, int max_total_len) {
     CK(cudaMalloc(&e->rope, tab.size() * sizeof(float2)));
     CK(cudaMemcpy(e->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
     e->rope_len = max_total_len;
+  }
+  {  // device-side layer table (weights + this request's KV pointers)
+    std::vector<LayerDev> h(nl);
+    for (size_t li = 0; li < nl; ++li) {
+      const LayerW& w = e->layers[li];
+      h[li] = LayerDev{w.attn_norm, w.wqkv, w.wo, w.mlp_norm, w.wgu, w.wdown,
+                       e->kv + (li * 2 + 0) * (size_t)c.n_kv_heads * e->L * c.head_dim,
+                       e->kv + (li * 2 + 1) * (size_t)c.n_kv_heads * e->L * c.head_dim};
+    }
+    if (!e->d_layers) CK(cudaMalloc(&e->d_layers, nl * sizeof(LayerDev)));
+    CK(cudaMemcpy(e->d_layers, h.data(), nl * sizeof(LayerDev), cudaMemcpyHostToDevice));
   }
   // reset_caches (llm_utils.py:409-414): zero like torchtune's KVCache.reset
   CK(cudaMemsetAsync(e->kv, 0, nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim * 2, e->stream));
@@ -712,10 +634,7 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
     CK(cudaGetLastError());
     e->launches++;
   }
-  for (int s = 0; s < n_tokens; ++s) {
-    if (int rc = launch_step(e, false, pos0 + s, s, s == n_tokens - 1, st)) return rc;
-    if (!e->last) CK(cudaMemcpyAsync(e->stage_out + (size_t)s * D, e->x, D * 2, cudaMemcpyDeviceToDevice, st));
-  }
+  if (int rc = launch_mega(e, 1, n_tokens, 0, pos0, st)) return rc;   // one launch walks all n_tokens positions
   if (e->last) {
     CK(cudaMemcpyAsync(out_f32, e->logits, (size_t)e->cfg.vocab * 4, cudaMemcpyDeviceToHost, st));
   } else {
@@ -750,7 +669,6 @@ int xotb200_inbox_export(xotb200_engine* e, void* out) {
 }
 
 static void drop_next(xotb200_engine* e) {
-  if (e->ring_graph) { cudaGraphExecDestroy(e->ring_graph); e->ring_graph = nullptr; }
   if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
   e->next_inbox = nullptr;
   e->next_ipc = false;
@@ -806,27 +724,9 @@ int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0) {
   if (int rc = xotb200_check_loaded(e)) return rc;
   CK(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
-  if (!e->ring_graph) {
-    cudaGraph_t g = nullptr;
-    const int64_t before = e->launches;
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = launch_step(e, true, 0, 0, true, st);
-    cudaError_t er = cudaStreamEndCapture(st, &g);
-    e->launches = before;
-    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-    CK(er);
-    er = cudaGraphInstantiate(&e->ring_graph, g, 0);
-    cudaGraphDestroy(g);
-    CK(er);
-  }
-  const int nl = e->end - e->start + 1;
-  const int per_step = 1 + 5 * nl + (e->last ? 1 : 0);
-  set_ctl_kernel<<<1, 1, 0, st>>>(e->ctl, pos0, step0, step0);
-  CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev0, st));
-  for (int i = 0; i < n_steps; ++i) CK(cudaGraphLaunch(e->ring_graph, st));
+  if (int rc = launch_mega(e, 0, n_steps, step0, pos0, st)) return rc;
   CK(cudaEventRecord(e->ev1, st));
-  e->launches += 1 + (int64_t)per_step * n_steps;
   e->last_ring_steps = n_steps;
   return 0;
 }
