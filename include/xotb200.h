@@ -121,6 +121,15 @@ int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float
  * t_out = result posted.  Arrays of n_steps uint64 each (hop latency accounting). */
 int xotb200_ring_timestamps(xotb200_engine* e, uint64_t* t_in, uint64_t* t_out, int n_steps);
 
+/* ---- tuning / debugging ----
+ * Limit the persistent kernel to max_ctas CTAs (0 = one per SM).  Needed when several engines share ONE GPU and run
+ * ring mode concurrently: their persistent kernels must be co-resident (sum of limits <= SM count). */
+int xotb200_set_cta_limit(xotb200_engine* e, int max_ctas);
+/* Per-op device timeline of CTA `cta` at ring step `step` (-1 disables): for op i the four globaltimer stamps
+ * [prologue start, tiles start, tiles done, barrier exit] at out[4*i..4*i+3].  Call once to arm (out may be NULL),
+ * run the ring, call again to read. */
+int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, int n_u64);
+
 /* ---- introspection ---- */
 int xotb200_kernel_launches(xotb200_engine* e, int64_t* count); /* kernels launched by this engine so far */
 int xotb200_weight_bytes(xotb200_engine* e, int64_t* bytes);    /* resident weight bytes of the current shard */

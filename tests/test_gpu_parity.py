@@ -131,7 +131,11 @@ def test_ring_mode_equals_api_mode(split):
   n_gen = 20
   ids_api, _ = _api_generate(_native(shape_name, [(0, shape.n_layers - 1)]), prompt, n_gen)
   engines = _native(shape_name, split)
+  import torch
+  n_sm = torch.cuda.get_device_properties(0).multi_processor_count
   for i, e in enumerate(engines):
+    if len(engines) > 1:          # persistent kernels of several engines on ONE GPU must be co-resident
+      e.set_cta_limit(n_sm // len(engines))
     e.link_next_local(engines[(i + 1) % len(engines)])
     e.begin_request(prompt.shape[1] + n_gen + 1)
   data = prompt.astype(np.int32)

@@ -32,3 +32,22 @@ for it in range(3):
   print(json.dumps({"iter": it, "prefill_s": round(tp, 3), "decode_ms": round(ms, 2), "tok_s": round(n_gen / ms * 1e3, 1),
                     "ms_per_tok": round(ms / n_gen, 4), "achieved_GBs": round(gbs, 1), "first_ids": toks[:8].tolist(),
                     "launches": e.kernel_launches()}), flush=True)
+
+if len(sys.argv) > 4:   # timeline of one ring step
+  e.debug_timeline(200, int(sys.argv[4]))
+  e.begin_request(n_prompt + n_gen + 1)
+  e.forward(prompt, 0); e.post_to_next(step0); e.ring_launch(n_gen, step0, n_prompt); e.ring_wait(n_gen); step0 += n_gen
+  tl = e.debug_timeline(-1, 0, read=True).astype(np.int64)
+  nops = 4 * shape.n_layers + 1
+  landed = tl[nops + 1: 2 * nops + 1, 0]
+  tl = tl[:nops]
+  names = ["qkv", "o", "gu", "down"]
+  pro = tl[:, 1] - tl[:, 0]; tiles = tl[:, 2] - tl[:, 1]; bar = tl[:, 3] - tl[:, 2]
+  gap = np.concatenate([tl[1:, 0] - tl[:-1, 3], [0]])
+  for k in range(4):
+    sel = np.arange(k, nops - 1, 4)
+    print(f"{names[k]:5s} prologue {pro[sel].mean()/1e3:6.2f} us  tiles {tiles[sel].mean()/1e3:6.2f} us  barrier(+attn) {bar[sel].mean()/1e3:6.2f} us  publish-gap {gap[sel].mean()/1e3:5.2f} us")
+  for k in range(4):
+    print(names[k], "landed stages at consume start (first 6 layers):", landed[k:24:4].tolist(), "mean", landed[k:nops-1:4].mean())
+  print(f"head  prologue {pro[-1]/1e3:6.2f} us  tiles {tiles[-1]/1e3:6.2f} us  barrier {bar[-1]/1e3:6.2f} us")
+  print("step total us", (tl[-1, 3] - tl[0, 0]) / 1e3, " sum prologue", pro.sum() / 1e3, " tiles", tiles.sum() / 1e3, " barrier", bar.sum() / 1e3)

@@ -110,6 +110,9 @@ struct xotb200_engine {
   void* mega = nullptr;
   size_t mega_smem = 0;
   int mega_xbuf = 0, mega_grid = 0;
+  int cta_limit = 0;
+  unsigned long long* dbg = nullptr;
+  int dbg_step = -1, dbg_cta = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   int last_ring_steps = 0;
@@ -151,18 +154,21 @@ static int prepare_mega(xotb200_engine* e) {
   mega_fn fn = pick_mega(tk, c.head_dim, R);
   REQUIRE(fn != nullptr, "no megakernel instantiation for tk=%d head_dim=%d gqa=%d", tk, c.head_dim, R);
   const size_t kmax = (size_t)std::max(std::max(c.dim, c.ffn), qdim);
-  const size_t attn_scratch = ((size_t)NW * R * 2 + (size_t)NW * R * c.head_dim) * 4;
+  const size_t attn_scratch = ((size_t)NCW * R * 2 + (size_t)NCW * R * c.head_dim) * 4;
   const size_t xbuf = align_up(std::max(kmax * 2, attn_scratch), 128);
-  const size_t smem = (size_t)NW * MK_S * MK_TR * tk * 2 + xbuf + (size_t)NW * MK_S * 8 + 256;
+  const size_t smem = (size_t)MK_NSTAGE * MK_STAGE_BYTES + xbuf + (size_t)(2 * MK_NSTAGE + 2 * MK_NSLOT) * 8 +
+                      (size_t)MK_NSLOT * NCW * 4 * 4 + 128 + 128;
   REQUIRE(smem <= SMEM_BUDGET, "shared memory %zu > %zu: activation width %zu too large for the ring", smem, SMEM_BUDGET, kmax);
   CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, GEMV_THREADS, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, MK_THREADS, smem));
   REQUIRE(per_sm >= 1, "megakernel does not fit on an SM");
   e->mega = (void*)fn;
   e->mega_smem = smem;
   e->mega_xbuf = (int)xbuf;
   e->mega_grid = e->sm_count;   // one CTA per SM, all co-resident (cooperative launch checks it)
+  if (e->cta_limit > 0) e->mega_grid = std::min(e->mega_grid, e->cta_limit);
+  e->nsplit = std::max(1, std::min(32, e->mega_grid / c.n_kv_heads));
   return 0;
 }
 
@@ -185,9 +191,10 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
   a.src_tokens = e->stage_tokens; a.src_hidden = e->stage_in; a.out_hidden = e->stage_out;
   a.xbuf_bytes = e->mega_xbuf;
+  a.dbg = (mode == 0 && e->dbg_step >= 0) ? e->dbg : nullptr; a.dbg_step = e->dbg_step; a.dbg_cta = e->dbg_cta;
   CK(cudaMemsetAsync(e->bar_counter, 0, 4, st));
   void* params[] = {&a};
-  CK(cudaLaunchCooperativeKernel((const void*)e->mega, dim3(e->mega_grid), dim3(GEMV_THREADS), params, e->mega_smem, st));
+  CK(cudaLaunchCooperativeKernel((const void*)e->mega, dim3(e->mega_grid), dim3(MK_THREADS), params, e->mega_smem, st));
   e->launches++;
   return 0;
 }
@@ -318,7 +325,13 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   REQUIRE(R == 1 || R == 2 || R == 4 || R == 8, "GQA ratio %d unsupported", R);
   REQUIRE(cfg->dim % 512 == 0 && cfg->ffn % 512 == 0 && (cfg->n_heads * cfg->head_dim) % 512 == 0,
           "dim, ffn and n_heads*head_dim must be multiples of 512");
-  REQUIRE(cfg->vocab % 4 == 0, "vocab must be a multiple of 4");
+  {  // rows per ring stage: 4 when every K is a multiple of 2048, else 16 (tiny shapes); every N must divide
+    const int qd = cfg->n_heads * cfg->head_dim;
+    const int tr = (cfg->dim % 2048 == 0 && cfg->ffn % 2048 == 0 && qd % 2048 == 0) ? 4 : 16;
+    const int nqkv = (cfg->n_heads + 2 * cfg->n_kv_heads) * cfg->head_dim;
+    REQUIRE(cfg->vocab % tr == 0 && cfg->dim % tr == 0 && (2 * cfg->ffn) % tr == 0 && nqkv % tr == 0,
+            "vocab, dim, 2*ffn and (n_heads+2*n_kv_heads)*head_dim must be multiples of %d", tr);
+  }
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
@@ -368,7 +381,7 @@ int xotb200_destroy(xotb200_engine* e) {
   free_shard(e);
   if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
   void* ptrs[] = {e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
-                  e->cta_best_idx, e->ctl, e->bar_counter, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
+                  e->cta_best_idx, e->ctl, e->bar_counter, e->dbg, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
                   e->stage_f32, e->stage_in, e->stage_out};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -757,6 +770,29 @@ int xotb200_ring_timestamps(xotb200_engine* e, uint64_t* t_in, uint64_t* t_out, 
   CK(cudaSetDevice(e->device));
   CK(cudaMemcpy(t_in, e->t_in, (size_t)n_steps * 8, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(t_out, e->t_out, (size_t)n_steps * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int xotb200_set_cta_limit(xotb200_engine* e, int max_ctas) {
+  REQUIRE(e && max_ctas >= 0, "bad argument");
+  REQUIRE(max_ctas == 0 || max_ctas >= e->cfg.n_kv_heads, "cta limit must be 0 (off) or >= n_kv_heads");
+  e->cta_limit = max_ctas;
+  e->mega = nullptr;   // re-resolve grid / splits on the next launch
+  return 0;
+}
+
+int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, int n_u64) {
+  REQUIRE(e, "null engine");
+  CK(cudaSetDevice(e->device));
+  const size_t cap = (size_t)(4 * e->cfg.n_layers + 2) * 4 * 2;
+  if (!e->dbg) { CK(cudaMalloc(&e->dbg, cap * 8)); CK(cudaMemset(e->dbg, 0, cap * 8)); }
+  if (out) {
+    REQUIRE(n_u64 >= 0 && (size_t)n_u64 <= cap, "n_u64 too large (max %zu)", cap);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, e->dbg, (size_t)n_u64 * 8, cudaMemcpyDeviceToHost));
+  }
+  e->dbg_step = step;
+  e->dbg_cta = cta;
   return 0;
 }
 

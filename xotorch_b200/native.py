@@ -158,6 +158,18 @@ class NativeShard:
     check(self.lib.xotb200_ring_timestamps(self.h, t_in.ctypes.data_as(C.c_void_p), t_out.ctypes.data_as(C.c_void_p), n_steps))
     return t_in, t_out
 
+  def set_cta_limit(self, max_ctas: int):
+    check(self.lib.xotb200_set_cta_limit(self.h, int(max_ctas)))
+
+  def debug_timeline(self, step: int, cta: int = 0, read: bool = False):
+    n = (4 * self.cfg.n_layers + 2) * 4 * 2
+    if read:
+      out = np.zeros(n, dtype=np.uint64)
+      check(self.lib.xotb200_debug_timeline(self.h, int(step), int(cta), out.ctypes.data_as(C.c_void_p), n))
+      return out.reshape(-1, 4)
+    check(self.lib.xotb200_debug_timeline(self.h, int(step), int(cta), None, 0))
+    return None
+
   # -- introspection ---------------------------------------------------------------------------------------------
   def kernel_launches(self) -> int:
     v = C.c_int64()
