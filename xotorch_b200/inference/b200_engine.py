@@ -1,0 +1,196 @@
+"""`B200ShardInferenceEngine` — the drop-in replacement for `TorchDynamicShardInferenceEngine`
+(/root/reference/xotorch/inference/torch/sharded_inference_engine.py:37-424) on B200.
+
+Same public surface (`encode / sample / decode / infer_tensor / ensure_shard / load_checkpoint`, attributes `.shard`,
+`.tokenizer`, `.shard_downloader`), same ndim protocol (2 => int token ids [1,S], 3 => float32 hidden [1,S,D]; returns
+float32 hidden [1,S,D] or last-position logits [1,V]), same 1-thread executor discipline — but every FLOP runs in
+libxotb200.so through the C ABI (xotorch_b200/native.py).  There is no CPU fallback.
+
+Deliberate deviations from reference DEFECTS: the inference_state that rides the ring is the tiny
+dict {"curr_pos": int} instead of the JSON-encoded L x L mask (B5/B11, §0.9); a shard hands off the output of its
+last layer (B1); KV capacity comes from the request (B7); strict weight loading (B6)."""
+from __future__ import annotations
+
+import asyncio
+import functools
+import os
+import uuid
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+
+from .inference_engine import InferenceEngine
+from .shard import Shard
+from .tokenizers import resolve_local_tokenizer
+
+TEMP = 0.6      # sharded_inference_engine.py:34
+TOP_K = 35      # sharded_inference_engine.py:35
+MAX_GENERATED_TOKENS = 1024   # general_mha.py:152: KV length = prompt + 1024
+
+
+def reference_sample(logits: np.ndarray, temp: float, top_k: int, q: np.ndarray) -> np.ndarray:
+  """torchtune.generation.sample restated on host arrays: /max(temp,1e-5), top-k mask,
+  softmax, argmax(probs / q).  `q` ~ Exp(1) noise.  Returns int32 [B,1]."""
+  x = logits.astype(np.float32) / np.float32(max(temp, 1e-5))
+  if top_k is not None:
+    k = min(int(top_k), x.shape[-1])
+    pivot = np.partition(x, -k, axis=-1)[..., -k][..., None]
+    x = np.where(x < pivot, -np.inf, x)
+  x = x - x.max(axis=-1, keepdims=True)
+  p = np.exp(x)
+  p = p / p.sum(axis=-1, keepdims=True)
+  return np.argmax(p / q, axis=-1).astype(np.int32).reshape(-1, 1)
+
+
+class LocalDirDownloader:
+  """Stands in for the reference's ShardDownloader (xotorch/download/shard_download.py:9-37): `ensure_shard` must
+  return a local directory.  There is no network on the B200 box, so model ids map to local directories."""
+
+  def __init__(self, model_dirs: Optional[Dict[str, os.PathLike]] = None):
+    self.model_dirs = dict(model_dirs or {})
+
+  async def ensure_shard(self, shard, inference_engine_name: str) -> Path:
+    mid = shard.model_id
+    if mid in self.model_dirs:
+      return Path(self.model_dirs[mid])
+    if Path(mid).is_dir():
+      return Path(mid)
+    env = os.environ.get("XOT_B200_MODEL_DIR")
+    if env and (Path(env) / mid).is_dir():
+      return Path(env) / mid
+    raise FileNotFoundError(f"no local model directory for model id {mid!r} (set model_dirs or XOT_B200_MODEL_DIR)")
+
+
+class B200ShardInferenceEngine(InferenceEngine):
+  def __init__(self, shard_downloader=None, device: Optional[int] = None,
+               native_factory: Optional[Callable] = None):
+    self.shard: Optional[Shard] = None
+    self.shard_downloader = shard_downloader if shard_downloader is not None else LocalDirDownloader()
+    self.tokenizer = None
+    self.native = None
+    self.model_path: Optional[Path] = None
+    self.model_config: Optional[dict] = None
+    self.request_id: Optional[str] = None
+    self.executor = ThreadPoolExecutor(max_workers=1)       # sharded_inference_engine.py:46
+    self.uuid = str(uuid.uuid4())
+    if device is None:
+      dev = os.environ.get("TORCH_DEVICE", "cuda:0")        # same env the reference honours (:58-59)
+      device = int(dev.split(":")[1]) if ":" in dev else 0
+    self.device = device
+    self._native_factory = native_factory                   # tests inject a stand-in; default = the CUDA library
+    self._kv_capacity = 0
+    self._pos = 0
+    import torch
+    self._rng = torch.Generator(device="cpu")
+    self._rng.manual_seed(1234)                             # sharded_inference_engine.py:67-69
+
+  # ---- helpers -------------------------------------------------------------------------------------------------
+  async def _run(self, fn, *a):
+    return await asyncio.get_running_loop().run_in_executor(self.executor, functools.partial(fn, *a))
+
+  def _make_native(self, hf_config: dict):
+    if self._native_factory is not None:
+      return self._native_factory(hf_config, self.device)
+    from xotorch_b200.native import NativeShard             # raises ImportError if libxotb200.so is missing
+    return NativeShard(hf_config, self.device)
+
+  # ---- reference API ---------------------------------------------------------------------------------------------
+  async def ensure_shard(self, shard: Shard):
+    """sharded_inference_engine.py:372-421: no-op for the same shard, else (re)load config, tokenizer, weights."""
+    if self.shard == shard:
+      return
+    from xotorch_b200.native import load_hf_config
+    self.model_path = Path(await self.shard_downloader.ensure_shard(shard, self.__class__.__name__))
+    self.model_config = load_hf_config(self.model_path)
+    if self.model_config["num_hidden_layers"] != shard.n_layers:
+      raise ValueError(f"shard.n_layers={shard.n_layers} but the model has {self.model_config['num_hidden_layers']} layers")
+    self.tokenizer = resolve_local_tokenizer(self.model_path, self.model_config["vocab_size"])
+
+    def start_model():
+      if self.native is not None:
+        self.native.close()
+      self.native = self._make_native(self.model_config)
+      self.native.load_dir(self.model_path, shard.start_layer, shard.end_layer)   # strict loader
+      self._kv_capacity = 0
+    await self._run(start_model)
+    self.shard = shard
+    self._pos = 0
+
+  async def encode(self, shard: Shard, prompt: str) -> np.ndarray:
+    await self.ensure_shard(shard)
+    def enc():
+      ids = self.tokenizer.encode(prompt)
+      return np.asarray(ids, dtype=np.int64).reshape(-1)
+    return await self._run(enc)
+
+  async def decode(self, shard: Shard, tokens: np.ndarray) -> str:
+    await self.ensure_shard(shard)
+    return await self._run(self.tokenizer.decode, np.asarray(tokens).reshape(-1).tolist())
+
+  async def sample(self, x: np.ndarray, temp=TEMP, top_k=TOP_K) -> np.ndarray:
+    """sharded_inference_engine.py:208-228.  Node calls sample(result, temp=0.0) (node.py:121): that is argmax except
+    on exact ties, which the seeded Exp(1) noise decides — reproduced bit for bit with the same CPU generator."""
+    def samp():
+      import torch
+      logits = np.asarray(x, dtype=np.float32).reshape(-1, x.shape[-1])
+      q = torch.empty((logits.shape[0], logits.shape[1])).exponential_(1, generator=self._rng).numpy()
+      return reference_sample(logits, temp, top_k, q)
+    return await self._run(samp)
+
+  async def infer_tensor(self, request_id: str, shard: Shard, input_data: np.ndarray,
+                         inference_state: Optional[dict] = None) -> Tuple[np.ndarray, Optional[dict]]:
+    """sharded_inference_engine.py:230-370.  Position protocol: only `curr_pos` crosses the hop; as in the reference
+    (:356-359) only the LAST shard advances it.  `inference_state is None` (or curr_pos == 0) starts a new request:
+    KV and position are reset (what `encode` does on the first shard, :133-147)."""
+    await self.ensure_shard(shard)
+    input_data = np.asarray(input_data)
+    if input_data.ndim not in (2, 3):
+      raise ValueError(f"input_data.ndim must be 2 (token ids) or 3 (hidden state), got {input_data.ndim}")
+    start_pos = int(inference_state["curr_pos"]) if inference_state and "curr_pos" in inference_state else 0
+    n = input_data.shape[1]
+    self.request_id = request_id
+
+    def step():
+      if start_pos == 0:
+        need = n + MAX_GENERATED_TOKENS
+        extra = int((inference_state or {}).get("max_total_len", 0))
+        self.native.begin_request(max(need, extra))
+        self._kv_capacity = max(need, extra)
+      out = self.native.forward(input_data, start_pos)
+      return out
+    out = await self._run(step)
+    if shard.is_last_layer():
+      new_pos = n if start_pos == 0 else start_pos + 1
+    else:
+      new_pos = start_pos
+    self._pos = new_pos
+    return out, {"curr_pos": new_pos}
+
+  async def load_checkpoint(self, shard: Shard, path: str):
+    await self.ensure_shard(shard)                          # sharded_inference_engine.py:423-424
+
+
+def register_with_xotorch() -> bool:
+  """Install this engine into an importable reference package (no plugin registry exists upstream: the factory is an
+  if/elif and model cards are keyed by engine CLASS NAME — SURVEY.md §8b).  Returns False if xotorch is absent."""
+  try:
+    import xotorch.inference.inference_engine as ref_ie
+    import xotorch.models as ref_models
+  except Exception:
+    return False
+  ref_ie.InferenceEngine.register(B200ShardInferenceEngine)
+  ref_ie.inference_engine_classes["b200"] = "B200ShardInferenceEngine"
+  orig = ref_ie.get_inference_engine
+
+  def patched(name, shard_downloader):
+    if name == "b200":
+      return B200ShardInferenceEngine(shard_downloader)
+    return orig(name, shard_downloader)
+  ref_ie.get_inference_engine = patched
+  for card in ref_models.model_cards.values():
+    repo = card.get("repo", {})
+    if "TorchDynamicShardInferenceEngine" in repo:          # same HF repos; a local dir is resolved by LocalDirDownloader
+      repo.setdefault("B200ShardInferenceEngine", repo["TorchDynamicShardInferenceEngine"])
+  return True
