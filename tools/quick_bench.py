@@ -37,8 +37,10 @@ if len(sys.argv) > 4:   # timeline of one ring step
   e.debug_timeline(200, int(sys.argv[4]))
   e.begin_request(n_prompt + n_gen + 1)
   e.forward(prompt, 0); e.post_to_next(step0); e.ring_launch(n_gen, step0, n_prompt); e.ring_wait(n_gen); step0 += n_gen
-  tl = e.debug_timeline(-1, 0, read=True).astype(np.int64)
+  raw = e.debug_timeline(-1, 0, read=True).astype(np.int64)
   nops = 4 * shape.n_layers + 1
+  stg = raw[(2 * nops + 2) * 4:(2 * nops + 2) * 4 + 256].reshape(4, 64)
+  tl = raw[:(2 * nops + 2) * 4].reshape(-1, 4)
   landed = tl[nops + 1: 2 * nops + 1, 0]
   tl = tl[:nops]
   names = ["qkv", "o", "gu", "down"]
@@ -50,4 +52,8 @@ if len(sys.argv) > 4:   # timeline of one ring step
   for k in range(4):
     print(names[k], "landed stages at consume start (first 6 layers):", landed[k:24:4].tolist(), "mean", landed[k:nops-1:4].mean())
   print(f"head  prologue {pro[-1]/1e3:6.2f} us  tiles {tiles[-1]/1e3:6.2f} us  barrier {bar[-1]/1e3:6.2f} us")
+  for k in range(4):
+    row = stg[k]; row = row[row > 0]
+    t0 = tl[20 + k, 1]
+    print(names[k], "stage arrival (us after consume start):", [round((v - t0) / 1e3, 2) for v in row[:16]])
   print("step total us", (tl[-1, 3] - tl[0, 0]) / 1e3, " sum prologue", pro.sum() / 1e3, " tiles", tiles.sum() / 1e3, " barrier", bar.sum() / 1e3)

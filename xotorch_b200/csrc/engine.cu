@@ -1,7 +1,10 @@
 // engine.cu — host side of libxotb200.so: engine object, weight layout + strict loader, request state, the step
 // launcher (direct mode and CUDA-graph ring mode) and the C ABI declared in include/xotb200.h.
 //
-// HBM layout of a shard (all bf16, 256-byte aligned, execution order so one decode step walks HBM linearly):
+// HBM layout of a shard (all bf16, 256-byte aligned, execution order so one decode step walks HBM linearly).
+// Every streamed matrix [N, K] is stored as K-panels [K/TK][N][TK]: any 8 consecutive rows of one K chunk — one ring
+// stage of the persistent kernel — are contiguous, so a stage is ONE TMA bulk copy of up to 32 KiB (the single producer
+// thread can issue only ~14 M bulk copies/s; with 4 KiB row-wise copies it could not outrun HBM).
 //   per layer: attn_norm[D] | Wqkv[(Hq+2Hkv)*hd, D] | Wo[D, Hq*hd] | mlp_norm[D] | Wgu[2F, D] | Wdown[D, F]
 //     Wqkv rows: q heads then k heads in interleaved-pair order (the reference's `_permute`,
 //       /root/reference/xotorch/inference/llm_utils.py:175-183) so a RoPE pair is two ADJACENT rows and the rotation
@@ -63,6 +66,8 @@ struct TensorSlot {
   int tensor_id;    // synth.py tensor id
   float std, mean;
   bool loaded;
+  int n_total;      // rows of the destination matrix
+  int panel_tk;     // 0: plain row-major; else K-panel layout [K/tk][n_total][tk] (streamed GEMV weights)
 };
 
 struct LayerW {
@@ -78,7 +83,8 @@ struct xotb200_engine {
   size_t blob_bytes = 0;
   std::vector<LayerW> layers;
   bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
-  std::map<std::string, TensorSlot> slots;
+  std::multimap<std::string, TensorSlot> slots;   // HF name -> destination(s) (a tied embedding feeds two)
+  int tk = 0;                                     // columns per ring stage, fixed per engine
   // request state
   bf16* kv = nullptr;
   int L = 0;
@@ -149,15 +155,16 @@ static int prepare_mega(xotb200_engine* e) {
   if (e->mega) return 0;
   const xotb200_model_cfg& c = e->cfg;
   const int qdim = c.n_heads * c.head_dim;
-  const int tk = (c.dim % 2048 == 0 && c.ffn % 2048 == 0 && qdim % 2048 == 0) ? 2048 : 512;
+  const int tk = e->tk;
+  REQUIRE(tk == 2048 || tk == 512, "no shard set");
   const int R = c.n_heads / c.n_kv_heads;
   mega_fn fn = pick_mega(tk, c.head_dim, R);
   REQUIRE(fn != nullptr, "no megakernel instantiation for tk=%d head_dim=%d gqa=%d", tk, c.head_dim, R);
   const size_t kmax = (size_t)std::max(std::max(c.dim, c.ffn), qdim);
   const size_t attn_scratch = ((size_t)NCW * R * 2 + (size_t)NCW * R * c.head_dim) * 4;
   const size_t xbuf = align_up(std::max(kmax * 2, attn_scratch), 128);
-  const size_t smem = (size_t)MK_NSTAGE * MK_STAGE_BYTES + xbuf + (size_t)(2 * MK_NSTAGE + 2 * MK_NSLOT) * 8 +
-                      (size_t)MK_NSLOT * NCW * 4 * 4 + 128 + 128;
+  const size_t smem = (size_t)mk_nstage(tk) * mk_stage_bytes(tk) + xbuf + (size_t)(2 * mk_nstage(tk) + 2 * MK_NSLOT) * 8 +
+                      (size_t)MK_NSLOT * NCW * 8 * 4 + 128 + 128;
   REQUIRE(smem <= SMEM_BUDGET, "shared memory %zu > %zu: activation width %zu too large for the ring", smem, SMEM_BUDGET, kmax);
   CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -280,6 +287,7 @@ static void free_shard(xotb200_engine* e) {
   if (e->kv) { cudaFree(e->kv); e->kv = nullptr; }
   e->layers.clear();
   e->slots.clear();
+  e->mega = nullptr;
   e->embed = e->final_norm = e->lm_head = nullptr;
   e->start = e->end = -1;
   e->L = 0;
@@ -287,7 +295,7 @@ static void free_shard(xotb200_engine* e) {
 
 static int upload_slot(xotb200_engine* e, TensorSlot& s, const void* host) {
   const size_t bytes = (size_t)s.rows * s.K * 2;
-  if (s.mode == 0 && s.stride == 1) {
+  if (s.mode == 0 && s.stride == 1 && s.panel_tk == 0) {
     CK(cudaMemcpyAsync(s.dst + (size_t)s.off * s.K, host, bytes, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
   } else {
@@ -295,7 +303,7 @@ static int upload_slot(xotb200_engine* e, TensorSlot& s, const void* host) {
     CK(cudaMalloc(&tmp, bytes));
     cudaError_t er = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, e->stream);
     if (er == cudaSuccess) {
-      relayout_rows_kernel<<<s.rows, 128, 0, e->stream>>>(tmp, s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off);
+      relayout_rows_kernel<<<s.rows, 128, 0, e->stream>>>(tmp, s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off, s.n_total, s.panel_tk);
       er = cudaGetLastError();
       e->launches++;
     }
@@ -325,13 +333,7 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   REQUIRE(R == 1 || R == 2 || R == 4 || R == 8, "GQA ratio %d unsupported", R);
   REQUIRE(cfg->dim % 512 == 0 && cfg->ffn % 512 == 0 && (cfg->n_heads * cfg->head_dim) % 512 == 0,
           "dim, ffn and n_heads*head_dim must be multiples of 512");
-  {  // rows per ring stage: 4 when every K is a multiple of 2048, else 16 (tiny shapes); every N must divide
-    const int qd = cfg->n_heads * cfg->head_dim;
-    const int tr = (cfg->dim % 2048 == 0 && cfg->ffn % 2048 == 0 && qd % 2048 == 0) ? 4 : 16;
-    const int nqkv = (cfg->n_heads + 2 * cfg->n_kv_heads) * cfg->head_dim;
-    REQUIRE(cfg->vocab % tr == 0 && cfg->dim % tr == 0 && (2 * cfg->ffn) % tr == 0 && nqkv % tr == 0,
-            "vocab, dim, 2*ffn and (n_heads+2*n_kv_heads)*head_dim must be multiples of %d", tr);
-  }
+  REQUIRE(cfg->vocab % 2 == 0, "vocab must be even (row pairs)");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
@@ -411,7 +413,11 @@ int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer) {
                sz_o = align_up(D * Hq * hd * 2, A), sz_gu = align_up(2 * F * D * 2, A), sz_dn = align_up(D * F * 2, A);
   const size_t per_layer = 2 * sz_norm + sz_qkv + sz_o + sz_gu + sz_dn;
   const size_t sz_emb = align_up(V * D * 2, A);
-  const bool own_head = e->last && !(c.tie_embeddings && e->first);
+  const bool own_head = e->last;   // the head is streamed in K-panel layout, the embedding is gathered row-wise: a tied
+                                   // model keeps both copies when one shard holds both
+  const int qdim = c.n_heads * c.head_dim;
+  e->tk = (c.dim % 2048 == 0 && c.ffn % 2048 == 0 && qdim % 2048 == 0) ? 2048 : 512;
+  const int tk = e->tk;
   size_t total = nl * per_layer + (e->first ? sz_emb : 0) + (e->last ? sz_norm : 0) + (own_head ? sz_emb : 0);
   CK(cudaMalloc(&e->blob, total));
   e->blob_bytes = total;
@@ -419,6 +425,7 @@ int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer) {
   auto take = [&](size_t n) { char* r = p; p += n; return reinterpret_cast<bf16*>(r); };
   if (e->first) e->embed = take(sz_emb);
   e->layers.resize(nl);
+  const int nqkv = (int)((Hq + 2 * Hkv) * hd);
   for (size_t li = 0; li < nl; ++li) {
     LayerW& w = e->layers[li];
     w.attn_norm = take(sz_norm); w.wqkv = take(sz_qkv); w.wo = take(sz_o);
@@ -426,33 +433,30 @@ int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer) {
     const int l = start_layer + (int)li;
     const std::string pre = "model.layers." + std::to_string(l) + ".";
     const int t = l * 16;
-    auto add = [&](const char* nm, bf16* dst, int rows, int K, int mode, int stride, int off, int kind, float mean) {
-      e->slots[pre + nm] = TensorSlot{dst, rows, K, mode, stride, off, t + kind, 0.02f, mean, false};
+    auto add = [&](const char* nm, bf16* dst, int rows, int K, int mode, int stride, int off, int kind, float mean,
+                   int n_total, int ptk) {
+      e->slots.insert({pre + nm, TensorSlot{dst, rows, K, mode, stride, off, t + kind, 0.02f, mean, false, n_total, ptk}});
     };
-    add("input_layernorm.weight", w.attn_norm, 1, (int)D, 0, 1, 0, 0, 1.0f);
-    add("self_attn.q_proj.weight", w.wqkv, (int)(Hq * hd), (int)D, 1, 1, 0, 1, 0.f);
-    add("self_attn.k_proj.weight", w.wqkv, (int)(Hkv * hd), (int)D, 1, 1, (int)(Hq * hd), 2, 0.f);
-    add("self_attn.v_proj.weight", w.wqkv, (int)(Hkv * hd), (int)D, 0, 1, (int)((Hq + Hkv) * hd), 3, 0.f);
-    add("self_attn.o_proj.weight", w.wo, (int)D, (int)(Hq * hd), 0, 1, 0, 4, 0.f);
-    add("post_attention_layernorm.weight", w.mlp_norm, 1, (int)D, 0, 1, 0, 5, 1.0f);
-    add("mlp.gate_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 0, 6, 0.f);
-    add("mlp.up_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 1, 7, 0.f);
-    add("mlp.down_proj.weight", w.wdown, (int)D, (int)F, 0, 1, 0, 8, 0.f);
+    add("input_layernorm.weight", w.attn_norm, 1, (int)D, 0, 1, 0, 0, 1.0f, 1, 0);
+    add("self_attn.q_proj.weight", w.wqkv, (int)(Hq * hd), (int)D, 1, 1, 0, 1, 0.f, nqkv, tk);
+    add("self_attn.k_proj.weight", w.wqkv, (int)(Hkv * hd), (int)D, 1, 1, (int)(Hq * hd), 2, 0.f, nqkv, tk);
+    add("self_attn.v_proj.weight", w.wqkv, (int)(Hkv * hd), (int)D, 0, 1, (int)((Hq + Hkv) * hd), 3, 0.f, nqkv, tk);
+    add("self_attn.o_proj.weight", w.wo, (int)D, (int)(Hq * hd), 0, 1, 0, 4, 0.f, (int)D, tk);
+    add("post_attention_layernorm.weight", w.mlp_norm, 1, (int)D, 0, 1, 0, 5, 1.0f, 1, 0);
+    add("mlp.gate_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 0, 6, 0.f, (int)(2 * F), tk);
+    add("mlp.up_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 1, 7, 0.f, (int)(2 * F), tk);
+    add("mlp.down_proj.weight", w.wdown, (int)D, (int)F, 0, 1, 0, 8, 0.f, (int)D, tk);
   }
   if (e->first)
-    e->slots["model.embed_tokens.weight"] = TensorSlot{e->embed, (int)V, (int)D, 0, 1, 0, (1 << 20), 0.02f, 0.f, false};
+    e->slots.insert({"model.embed_tokens.weight", TensorSlot{e->embed, (int)V, (int)D, 0, 1, 0, (1 << 20), 0.02f, 0.f, false, (int)V, 0}});
   if (e->last) {
     e->final_norm = take(sz_norm);
-    e->slots["model.norm.weight"] = TensorSlot{e->final_norm, 1, (int)D, 0, 1, 0, (1 << 20) + 1, 0.02f, 1.0f, false};
-    if (own_head) {
-      e->lm_head = take(sz_emb);
-      if (c.tie_embeddings)  // last-but-not-first shard of a tied model: the head IS the embedding table
-        e->slots["model.embed_tokens.weight"] = TensorSlot{e->lm_head, (int)V, (int)D, 0, 1, 0, (1 << 20), 0.02f, 0.f, false};
-      else
-        e->slots["lm_head.weight"] = TensorSlot{e->lm_head, (int)V, (int)D, 0, 1, 0, (1 << 20) + 2, 0.02f, 0.f, false};
-    } else {
-      e->lm_head = e->embed;
-    }
+    e->slots.insert({"model.norm.weight", TensorSlot{e->final_norm, 1, (int)D, 0, 1, 0, (1 << 20) + 1, 0.02f, 1.0f, false, 1, 0}});
+    e->lm_head = take(sz_emb);
+    if (c.tie_embeddings)   // tied: the head IS the embedding table (general_mha.py:42-44,125-126), stored again as K-panels
+      e->slots.insert({"model.embed_tokens.weight", TensorSlot{e->lm_head, (int)V, (int)D, 0, 1, 0, (1 << 20), 0.02f, 0.f, false, (int)V, tk}});
+    else
+      e->slots.insert({"lm_head.weight", TensorSlot{e->lm_head, (int)V, (int)D, 0, 1, 0, (1 << 20) + 2, 0.02f, 0.f, false, (int)V, tk}});
   }
   return 0;
 }
@@ -461,13 +465,16 @@ int xotb200_load_tensor(xotb200_engine* e, const char* hf_name, const void* host
   REQUIRE(e && hf_name && host_data && shape, "null argument");
   REQUIRE(e->start >= 0, "no shard set");
   CK(cudaSetDevice(e->device));
-  auto it = e->slots.find(hf_name);
-  if (it == e->slots.end()) return 1;  // not part of this shard
-  TensorSlot& s = it->second;
+  auto range = e->slots.equal_range(hf_name);
+  if (range.first == range.second) return 1;  // not part of this shard
   const int64_t rows = ndim == 2 ? shape[0] : 1, K = ndim == 2 ? shape[1] : shape[0];
-  REQUIRE((ndim == 1 || ndim == 2) && rows == s.rows && K == s.K, "tensor %s: shape mismatch (got %lld x %lld, want %d x %d)",
-          hf_name, (long long)rows, (long long)K, s.rows, s.K);
-  return upload_slot(e, s, host_data);
+  for (auto it = range.first; it != range.second; ++it) {
+    TensorSlot& s = it->second;
+    REQUIRE((ndim == 1 || ndim == 2) && rows == s.rows && K == s.K, "tensor %s: shape mismatch (got %lld x %lld, want %d x %d)",
+            hf_name, (long long)rows, (long long)K, s.rows, s.K);
+    if (int rc = upload_slot(e, s, host_data)) return rc;
+  }
+  return 0;
 }
 
 int xotb200_check_loaded(xotb200_engine* e) {
@@ -533,7 +540,7 @@ int xotb200_init_synthetic(xotb200_engine* e, uint64_t seed) {
     TensorSlot& s = kv.second;
     const unsigned long long base = seed * 0x9E3779B97F4A7C15ull + (unsigned long long)s.tensor_id * 0xD1B54A32D192ED03ull;
     const float scale = (float)((double)s.std / ih4_std);
-    synth_rows_kernel<<<s.rows, 256, 0, e->stream>>>(s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off, base, scale, s.mean);
+    synth_rows_kernel<<<s.rows, 256, 0, e->stream>>>(s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off, s.n_total, s.panel_tk, base, scale, s.mean);
     CK(cudaGetLastError());
     e->launches++;
     s.loaded = true;
@@ -784,7 +791,7 @@ int xotb200_set_cta_limit(xotb200_engine* e, int max_ctas) {
 int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, int n_u64) {
   REQUIRE(e, "null engine");
   CK(cudaSetDevice(e->device));
-  const size_t cap = (size_t)(4 * e->cfg.n_layers + 2) * 4 * 2;
+  const size_t cap = (size_t)(4 * e->cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8;
   if (!e->dbg) { CK(cudaMalloc(&e->dbg, cap * 8)); CK(cudaMemset(e->dbg, 0, cap * 8)); }
   if (out) {
     REQUIRE(n_u64 >= 0 && (size_t)n_u64 <= cap, "n_u64 too large (max %zu)", cap);

@@ -157,21 +157,29 @@ __global__ void post_kernel(InboxHdr* next, const bf16* hidden, int D, const int
   }
 }
 
-// Row re-layout while loading: dst row r <- src row map(r)
-//   mode 0: identity; mode 1: q/k interleave (_permute, llm_utils.py:175-183) with `hd`;
+// Row re-layout while loading: destination row rd = dst_row_off + r*dst_stride_rows takes source row map(r)
+//   mode 0: identity; mode 1: q/k interleave (_permute, llm_utils.py:175-183) with `hd`.
+// Destination layout: panel_tk == 0 -> plain row-major [n_total, K]; else K-panels [K/panel_tk][n_total][panel_tk]
+// (element (rd, c) at ((c / tk) * n_total + rd) * tk + c % tk) so that any run of consecutive rows of one K chunk is
+// contiguous: a whole ring stage of the persistent kernel is ONE TMA bulk copy.
+__device__ __forceinline__ size_t panel_index(int rd, int c, int K, int n_total, int tk) {
+  if (tk == 0) return (size_t)rd * K + c;
+  return ((size_t)(c / tk) * n_total + rd) * tk + (c % tk);
+}
+__device__ __forceinline__ int src_row_of(int r, int mode, int hd) {
+  if (mode != 1) return r;
+  const int h = r / hd, i = r % hd;
+  return h * hd + (i & 1) * (hd / 2) + (i >> 1);
+}
 __global__ void relayout_rows_kernel(const bf16* src, bf16* dst, int rows, int K, int mode, int hd, int dst_stride_rows,
-                                     int dst_row_off) {
-  // dst row index = dst_row_off + r * dst_stride_rows  (stride 2 interleaves gate/up)
+                                     int dst_row_off, int n_total, int panel_tk) {
   const int r = blockIdx.x;
   if (r >= rows) return;
-  int sr = r;
-  if (mode == 1) {
-    const int h = r / hd, i = r % hd;
-    sr = h * hd + (i & 1) * (hd / 2) + (i >> 1);
-  }
+  const int sr = src_row_of(r, mode, hd);
+  const int rd = dst_row_off + r * dst_stride_rows;
   const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)sr * K);
-  uint4* d4 = reinterpret_cast<uint4*>(dst + ((size_t)dst_row_off + (size_t)r * dst_stride_rows) * K);
-  for (int c = threadIdx.x; c < K / 8; c += blockDim.x) d4[c] = s4[c];
+  for (int c8 = threadIdx.x; c8 < K / 8; c8 += blockDim.x)
+    *reinterpret_cast<uint4*>(dst + panel_index(rd, c8 * 8, K, n_total, panel_tk)) = s4[c8];
 }
 
 // Counter-based synthetic weights, bit-identical to xotorch_b200/synth.py (splitmix64 -> Irwin-Hall(4)).
@@ -183,19 +191,16 @@ __device__ __forceinline__ float synth_value(unsigned long long base, unsigned l
   const int s = (int)(z & 0xffff) + (int)((z >> 16) & 0xffff) + (int)((z >> 32) & 0xffff) + (int)(z >> 48);
   return __fadd_rn(__fmul_rn((float)(s - 131070), scale), mean);
 }
-// dst row r (of `rows`) takes HF row map(r) of the tensor; same mapping as relayout_rows_kernel.
+// dst row (see relayout_rows_kernel) takes HF row map(r) of the tensor; same destination layouts.
 __global__ void synth_rows_kernel(bf16* dst, int rows, int K, int mode, int hd, int dst_stride_rows, int dst_row_off,
-                                  unsigned long long base, float scale, float mean) {
+                                  int n_total, int panel_tk, unsigned long long base, float scale, float mean) {
   const int r = blockIdx.x;
   if (r >= rows) return;
-  int sr = r;
-  if (mode == 1) {
-    const int h = r / hd, i = r % hd;
-    sr = h * hd + (i & 1) * (hd / 2) + (i >> 1);
-  }
-  bf16* d = dst + ((size_t)dst_row_off + (size_t)r * dst_stride_rows) * K;
+  const int sr = src_row_of(r, mode, hd);
+  const int rd = dst_row_off + r * dst_stride_rows;
   for (int c = threadIdx.x; c < K; c += blockDim.x)
-    d[c] = f2bf(synth_value(base, (unsigned long long)sr * (unsigned long long)K + c, scale, mean));
+    dst[panel_index(rd, c, K, n_total, panel_tk)] =
+        f2bf(synth_value(base, (unsigned long long)sr * (unsigned long long)K + c, scale, mean));
 }
 
 }  // namespace xb

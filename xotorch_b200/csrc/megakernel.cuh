@@ -28,9 +28,11 @@ constexpr int W_PROD = 8;                 // TMA producer warp
 constexpr int W_EPI = 9;                  // epilogue warp (cross-warp reduction + fused epilogues)
 constexpr int MK_THREADS = 320;
 constexpr int CONS_THREADS = NCW * 32;    // 256
-constexpr int MK_STAGE_BYTES = 16384;     // one ring stage: TR rows x TK columns of bf16
-constexpr int MK_NSTAGE = 12;             // CTA-level ring depth (192 KiB in flight per SM)
+constexpr int MK_ROWS = 8;                // weight rows per ring stage (4 RoPE / gate-up pairs)
 constexpr int MK_NSLOT = 4;               // partial-sum hand-off slots consumer warps -> epilogue warp
+__host__ __device__ constexpr int mk_stage_bytes(int tk) { return MK_ROWS * tk * 2; }
+__host__ __device__ constexpr int mk_nstage(int tk) { return tk >= 2048 ? 6 : 12; }   // ring depth: 192 KiB (Llama sizes) / 96 KiB (tiny)
+
 
 __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -98,12 +100,44 @@ __device__ __forceinline__ OpInfo op_info(const MegaArgs& a, int op) {
   return o;
 }
 
-// rows -> CTAs: contiguous groups of TR rows, balanced to +-1 group
-__device__ __forceinline__ void cta_groups(int N, int TR, int& g0, int& gn) {
-  const int ngroups = N / TR;
-  const int gpc = ngroups / gridDim.x, grem = ngroups % gridDim.x;
-  g0 = blockIdx.x * gpc + min((int)blockIdx.x, grem);
-  gn = gpc + ((int)blockIdx.x < grem ? 1 : 0);
+// acc (packed fp32x2) += 8 bf16 weights (one 16-byte shared-memory load) * 8 x values (4 packed fp32x2): 8 unpack ops
+// + 4 FFMA2 (Blackwell packed fp32 FMA).  Lane-local; the two halves of acc are added at the end of the row group.
+__device__ __forceinline__ float2 dot8_f2(const uint4& w, const float2 (&x)[4], float2 acc) {
+  acc = __ffma2_rn(make_float2(bf_lo(w.x), bf_hi(w.x)), x[0], acc);
+  acc = __ffma2_rn(make_float2(bf_lo(w.y), bf_hi(w.y)), x[1], acc);
+  acc = __ffma2_rn(make_float2(bf_lo(w.z), bf_hi(w.z)), x[2], acc);
+  acc = __ffma2_rn(make_float2(bf_lo(w.w), bf_hi(w.w)), x[3], acc);
+  return acc;
+}
+
+// Transpose-reduce NV per-lane values over the 32 lanes of a warp: NV-1 exchange shuffles + log2(32/NV) butterfly
+// steps (9 shuffles for NV=8 instead of 40).  Afterwards lane L holds the warp total of value index L / (32/NV).
+template <int NV>
+__device__ __forceinline__ float warp_reduce_rows(float (&v)[NV], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// rows -> CTAs: contiguous ranges of row PAIRS (RoPE / gate-up pairs stay together), balanced to +-1 pair
+__device__ __forceinline__ void cta_pairs(int N, int& p0, int& pn) {
+  const int npairs = N / 2;
+  const int ppc = npairs / gridDim.x, prem = npairs % gridDim.x;
+  p0 = blockIdx.x * ppc + min((int)blockIdx.x, prem);
+  pn = ppc + ((int)blockIdx.x < prem ? 1 : 0);
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -284,38 +318,45 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
 // ------------------------------------------------------------------------------------------------------------
 // the kernel: 10 warps = 8 consumers + 1 TMA producer + 1 epilogue
 //
-// Ring stage = TR rows x TK columns (16 KiB).  Column block cb (256 columns) of row subset rs (4 rows) belongs to
-// consumer warp rs*CB+cb, so EVERY consumer warp works on EVERY stage (K-split): perfect balance inside the CTA and
-// one in-order weight stream per SM.  Per row group the 8 warps hand their partial sums to the epilogue warp
-// through a 4-slot mbarrier mailbox; it adds them in fixed order (deterministic) and applies the fused epilogue.
-//   TK=2048: CB=8, RS=1, TR=4   (Llama-3 sizes)        TK=512: CB=2, RS=4, TR=16   (tiny parity shapes)
+// Ring stage = 8 weight rows x TK columns.  A CTA owns a contiguous range of row pairs and walks it in groups of 8
+// rows (the last group of an op may be shorter: only its real rows are loaded).  Every consumer warp works on EVERY
+// stage (K-split): column block cb (256 columns) of row subset rs belongs to warp rs*CB+cb — perfect balance inside
+// the CTA and one in-order weight stream per SM.  TK=2048: 8 warps x (8 rows x 256 cols); TK=512 (tiny parity
+// shapes): 4 row subsets x 2 column blocks, 2 rows per warp.  The inner loop is deliberately lean (the consumers must
+// drain the ring several times faster than HBM fills it, or stalls at barriers are never recovered): one 16-byte
+// shared load + 8 unpack + 4 packed FFMA2 per 8 weights, the x chunk converted once per stage, a 9-shuffle
+// transpose-reduce per row group.  Partials go to the epilogue warp through a 4-slot mbarrier mailbox; it adds them
+// in fixed order (deterministic) and applies the fused epilogue.
 // ------------------------------------------------------------------------------------------------------------
 template <int TK, int HD, int R>
 __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int CB = TK / 256;          // column blocks per stage
-  constexpr int RS = NCW / CB;          // row subsets per stage
-  constexpr int TR = 4 * RS;            // rows per stage
-  static_assert(TR * TK * 2 == MK_STAGE_BYTES, "stage must be 16 KiB");
+  constexpr int ROWB = TK * 2;                    // bytes per stage row
+  constexpr int STAGE_BYTES = mk_stage_bytes(TK);
+  constexpr int NSTAGE = mk_nstage(TK);
+  constexpr int CB = TK / 256;                    // column blocks per stage (a lane covers 8 columns, a warp 256)
+  constexpr int RS = NCW / CB;                    // row subsets per stage
+  constexpr int RPW = MK_ROWS / RS;               // rows per consumer warp per stage
+  static_assert(CB * RS == NCW && RPW * RS == MK_ROWS, "TK must be 256, 512, 1024 or 2048");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // smem: [ring][xbuf][full NSTAGE][empty NSTAGE][done NSLOT][free NSLOT][part NSLOT*NCW*4 f32][red 32 f32]
+  // smem: [ring][xbuf][full NSTAGE][empty NSTAGE][done NSLOT][free NSLOT][part NSLOT*NCW*8 f32][red 32 f32]
   uint8_t* ring = smem;
-  uint8_t* xbuf = smem + (size_t)MK_NSTAGE * MK_STAGE_BYTES;
+  uint8_t* xbuf = smem + (size_t)NSTAGE * STAGE_BYTES;
   bf16* x_s = reinterpret_cast<bf16*>(xbuf);
   uint64_t* full = reinterpret_cast<uint64_t*>(xbuf + a.xbuf_bytes);
-  uint64_t* empty = full + MK_NSTAGE;
-  uint64_t* done = empty + MK_NSTAGE;
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* done = empty + NSTAGE;
   uint64_t* freeb = done + MK_NSLOT;
-  float* part = reinterpret_cast<float*>(freeb + MK_NSLOT);   // [NSLOT][NCW][4]
-  float* red = part + MK_NSLOT * NCW * 4;
+  float* part = reinterpret_cast<float*>(freeb + MK_NSLOT);   // [NSLOT][NCW][8]
+  float* red = part + MK_NSLOT * NCW * 8;
   __shared__ volatile int s_abort;
   __shared__ int s_tok;
 
   const int nops_all = 4 * a.nl + (a.last ? 1 : 0);
   if (threadIdx.x == 0) {
     s_abort = 0;
-    for (int i = 0; i < MK_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
     for (int i = 0; i < MK_NSLOT; ++i) { mbar_init(&done[i], NCW); mbar_init(&freeb[i], 1); }
     fence_mbar_init();
   }
@@ -328,13 +369,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
 
   // =========================================== producer warp ===========================================
   // One cursor walks the tile list (step, op, row group, K chunk) of this CTA across ops and steps and feeds the
-  // shared-memory ring with TMA bulk copies; it only ever blocks on a full ring, never on a grid barrier.
-  // (An HBM->L2 prefetch cursor running ahead of the ring was tried and measured SLOWER on B200: every byte then
-  //  crosses the L2 twice and the L2-slice throughput, not HBM, becomes the cap.)
+  // shared-memory ring with ONE TMA bulk copy per stage (K-panel weight layout); it only ever blocks on a full ring,
+  // never on a grid barrier.  (HBM->L2 prefetch ahead of the ring — always, or only while the ring is full — was tried
+  // and measured SLOWER on B200: every byte then crosses the L2 twice and L2-slice throughput becomes the cap.)
   if (warp == W_PROD) {
     if (lane != 0) return;
     const uint64_t policy = policy_evict_first();
-    struct Cur { int s, op, g, kc, g0, gn, KC, K; const bf16* W; bool end; };
+    // tile cursor: (step, op, group, K chunk) of this CTA, flattened index `idx`
+    struct Cur { int s, op, g, kc, p0, pn, ng, KC, K, N; const bf16* W; unsigned int idx; bool end; };
     auto cur_seek = [&](Cur& c) {        // position on the first tile at or after (c.s, c.op)
       c.g = 0; c.kc = 0;
       while (true) {
@@ -342,49 +384,48 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
         if (c.op >= nops_all) { c.op = 0; ++c.s; continue; }
         if (!op_enabled(c.op, c.s)) { ++c.op; continue; }
         const OpInfo o = op_info(a, c.op);
-        cta_groups(o.N, TR, c.g0, c.gn);
-        if (c.gn == 0) { ++c.op; continue; }
-        c.W = o.W; c.K = o.K; c.KC = o.K / TK;
+        cta_pairs(o.N, c.p0, c.pn);
+        c.ng = (c.pn + 3) >> 2;
+        if (c.ng == 0) { ++c.op; continue; }
+        c.W = o.W; c.K = o.K; c.N = o.N; c.KC = o.K / TK;
         return;
       }
     };
     auto cur_next = [&](Cur& c) {
-      if (++c.kc == c.KC) { c.kc = 0; if (++c.g == c.gn) { ++c.op; cur_seek(c); } }
+      ++c.idx;
+      if (++c.kc == c.KC) { c.kc = 0; if (++c.g == c.ng) { ++c.op; cur_seek(c); } }
     };
-    Cur ld{0, 0, 0, 0, 0, 0, 1, 0, nullptr, false};
+    Cur ld{0, 0, 0, 0, 0, 0, 0, 1, 0, 0, nullptr, 0u, false};
     cur_seek(ld);
-    unsigned int p_cnt = 0;
     bool aborted = false;
     while (!ld.end) {
-      const int st = p_cnt % MK_NSTAGE;
-      const uint32_t par = ((p_cnt / MK_NSTAGE) & 1u) ^ 1u;
+      const unsigned int p_cnt = ld.idx;
+      const int st = p_cnt % NSTAGE;
+      const uint32_t par = ((p_cnt / NSTAGE) & 1u) ^ 1u;
       while (!mbar_try_wait(&empty[st], par)) {
         if (s_abort) { aborted = true; break; }
       }
       if (aborted) break;
-      uint8_t* dst = ring + (size_t)st * MK_STAGE_BYTES;
-      const size_t row0 = (size_t)(ld.g0 + ld.g) * TR;
-      mbar_expect_tx(&full[st], MK_STAGE_BYTES);
-      if (ld.KC == 1) {
-        bulk_g2s(dst, ld.W + row0 * ld.K, MK_STAGE_BYTES, &full[st], policy);
-      } else {
-#pragma unroll 4
-        for (int r = 0; r < TR; ++r)
-          bulk_g2s(dst + r * TK * 2, ld.W + (row0 + r) * ld.K + (size_t)ld.kc * TK, TK * 2, &full[st], policy);
-      }
-      ++p_cnt;
+      uint8_t* dst = ring + (size_t)st * STAGE_BYTES;
+      const size_t row0 = (size_t)(ld.p0 + 4 * ld.g) * 2;
+      const int nrows = min(MK_ROWS, 2 * (ld.pn - 4 * ld.g));
+      // K-panel layout [K/TK][N][TK]: the nrows x TK stage is contiguous in HBM -> ONE bulk copy of up to 32 KiB
+      mbar_expect_tx(&full[st], (uint32_t)nrows * TK * 2);
+      bulk_g2s(dst, ld.W + ((size_t)ld.kc * ld.N + row0) * TK, (uint32_t)nrows * TK * 2, &full[st], policy);
       cur_next(ld);
     }
     // never exit with bulk copies in flight: wait for the completion of everything issued and not yet consumed
-    const unsigned int lo = p_cnt > MK_NSTAGE ? p_cnt - MK_NSTAGE : 0;
-    for (unsigned int i = lo; i < p_cnt; ++i) mbar_wait(&full[i % MK_NSTAGE], (i / MK_NSTAGE) & 1u);
+    const unsigned int p_end = ld.idx;
+    const unsigned int lo = p_end > (unsigned)NSTAGE ? p_end - NSTAGE : 0;
+    for (unsigned int i = lo; i < p_end; ++i) mbar_wait(&full[i % NSTAGE], (i / NSTAGE) & 1u);
     return;
   }
 
   // ================================== consumer warps 0..7 and epilogue warp ==================================
   const bool is_epi = (warp == W_EPI);
-  const int cb = warp % CB, rs = warp / CB;      // consumer role
-  unsigned int c_cnt = 0;                         // stages consumed (consumers)
+  const int cb = warp % CB, rs = warp / CB;       // consumer role: column block, row subset
+  int c_st = 0;                                   // ring position of the next stage to consume (consumers)
+  uint32_t c_ph = 0;
   unsigned int g_cnt = 0;                         // row groups handed over (consumers) / finished (epilogue)
   unsigned int bar_target = 0;
   bool ok = true;
@@ -427,8 +468,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
       const OpInfo o = op_info(a, op);
       const LayerDev* lw = o.kind == OP_HEAD ? nullptr : &a.layers[o.li];
       const int K = o.K, KC = K / TK;
-      int g0, gn;
-      cta_groups(o.N, TR, g0, gn);
+      int p0, pn;
+      cta_pairs(o.N, p0, pn);
+      const int ngroups = (pn + 3) >> 2;
       if (dbg_on) a.dbg[op * 4 + 0] = globaltimer_ns();
 
       if (!is_epi) {
@@ -484,102 +526,119 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
         if (dbg_on) {
           a.dbg[op * 4 + 1] = globaltimer_ns();
           int landed = 0;    // ring stages already filled when consumption of this op starts
-          for (int i = 0; i < MK_NSTAGE; ++i)
-            landed += mbar_try_wait(&full[(c_cnt + i) % MK_NSTAGE], ((c_cnt + i) / MK_NSTAGE) & 1u) ? 1 : 0;
+          for (int i = 0; i < NSTAGE; ++i) {
+            const int si = (c_st + i) % NSTAGE;
+            landed += mbar_try_wait(&full[si], si >= c_st ? c_ph : (c_ph ^ 1u)) ? 1 : 0;
+          }
           a.dbg[(nops_all + 1 + op) * 4] = (unsigned long long)landed;
         }
-        // ---------------- consume: every warp takes its 4 rows x 256 columns of every stage ----------------
-        // Software pipelined: the registers of tile t+1 are loaded (and its stage released) before the FMAs of
-        // tile t, so mbarrier-wait + LDS latency of the next stage hides behind the math of the current one.
-        const int T = gn * KC;
-        const uint4* xs4 = reinterpret_cast<const uint4*>(x_s) + cb * 32 + lane;
-        const uint4* ring4 = reinterpret_cast<const uint4*>(ring) + (size_t)(rs * 4) * (TK / 8) + cb * 32 + lane;
-        auto load_tile = [&](unsigned int cnt, int kc, uint4 (&w)[4], uint4& xv) {
-          const int st = cnt % MK_NSTAGE;
-          mbar_wait(&full[st], (cnt / MK_NSTAGE) & 1u);
-          const uint4* t4 = ring4 + (size_t)st * (MK_STAGE_BYTES / 16);
+        // ---------------- consume: every warp takes its RPW rows x 256 columns of every stage ----------------
+        // Software pipeline over the CTA's tile list of this op: the registers of tile t+1 are loaded before the math of
+        // tile t is issued and its stage is released after that math (the loads have long completed, so the release
+        // never stalls); the row-group reduction + mailbox hand-off of group g overlaps the loads of group g+1.
+        const uint8_t* wlane = ring + (size_t)(rs * RPW) * ROWB + (size_t)(cb * 256 + lane * 8) * 2;
+        const bf16* xlane = x_s + cb * 256 + lane * 8;
+        const int T = ngroups * KC;
+        float2 acc[RPW];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) w[r] = t4[r * (TK / 8)];
-          xv = xs4[kc * (TK / 8)];
+        for (int r = 0; r < RPW; ++r) acc[r] = make_float2(0.f, 0.f);
+        int ld_st = c_st;                  // ring slot of the tile whose registers were loaded last
+        auto load_tile = [&](int kc, uint4 (&w)[RPW], uint4& xv) {
+          mbar_wait(&full[c_st], c_ph);
+          const uint8_t* wp = wlane + (size_t)c_st * STAGE_BYTES;
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) w[r] = *reinterpret_cast<const uint4*>(wp + r * ROWB);
+          xv = *reinterpret_cast<const uint4*>(xlane + (size_t)kc * TK);
+          ld_st = c_st;
+          if (++c_st == NSTAGE) { c_st = 0; c_ph ^= 1u; }
+        };
+        auto release = [&](int st) {       // all lanes' loads of that stage are complete by now
           __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[st]);   // release: the tile now lives in registers
+          if (lane == 0) mbar_arrive(&empty[st]);
         };
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        auto compute = [&](const uint4 (&w)[RPW], const uint4& xv) {
+          float2 xf[4];
+          xf[0] = make_float2(bf_lo(xv.x), bf_hi(xv.x)); xf[1] = make_float2(bf_lo(xv.y), bf_hi(xv.y));
+          xf[2] = make_float2(bf_lo(xv.z), bf_hi(xv.z)); xf[3] = make_float2(bf_lo(xv.w), bf_hi(xv.w));
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) acc[r] = dot8_f2(w[r], xf, acc[r]);
+        };
         auto finish_group = [&]() {
+          float v[RPW];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
-          if (lane == 0) {
-            const int ps = g_cnt % MK_NSLOT;
-            mbar_wait(&freeb[ps], ((g_cnt / MK_NSLOT) & 1u) ^ 1u);
-            *reinterpret_cast<float4*>(part + (ps * NCW + warp) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            mbar_arrive(&done[ps]);
-          }
+          for (int r = 0; r < RPW; ++r) { v[r] = acc[r].x + acc[r].y; acc[r] = make_float2(0.f, 0.f); }
+          const int ps = g_cnt % MK_NSLOT;
+          const uint32_t fpar = ((g_cnt / MK_NSLOT) & 1u) ^ 1u;
+          const float tot = warp_reduce_rows<RPW>(v, lane);       // lane L: total of row L / (32/RPW)
+          mbar_wait(&freeb[ps], fpar);                            // all lanes poll (uniform): no divergent wait
+          if ((lane & (32 / RPW - 1)) == 0) part[(ps * NCW + warp) * 8 + lane / (32 / RPW)] = tot;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&done[ps]);
           ++g_cnt;
-#pragma unroll
-          for (int r = 0; r < 4; ++r) acc[r] = 0.f;
         };
-        auto compute = [&](const uint4 (&w)[4], const uint4& xv) {
-          float xf[8];
-          unpack8(xv, xf);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) acc[r] = dot8(w[r], xf, acc[r]);
-        };
-        uint4 wA[4], wB[4], xA, xB;
-        int kcA = 0;                       // K-chunk index of the tile held in A
-        if (T > 0) load_tile(c_cnt, 0, wA, xA);
+        uint4 wA[RPW], wB[RPW], xA, xB;
+        int kcA = 0, stA = 0, stB = 0;
+        if (T > 0) { load_tile(0, wA, xA); stA = ld_st; }
         for (int t = 0; t < T; t += 2) {
-          // ---- tile t in A; prefetch t+1 into B ----
           const int kcB = (kcA + 1 == KC) ? 0 : kcA + 1;
-          if (t + 1 < T) load_tile(c_cnt + 1, kcB, wB, xB);
+          if (t + 1 < T) { load_tile(kcB, wB, xB); stB = ld_st; }
           compute(wA, xA);
-          ++c_cnt;
+          release(stA);
+          if (dbg_on && op >= 20 && op < 24 && t < 60) a.dbg[(2 * nops_all + 2) * 4 + (op - 20) * 64 + t] = globaltimer_ns();
           if (kcA == KC - 1) finish_group();
           if (t + 1 >= T) break;
-          // ---- tile t+1 in B; prefetch t+2 into A ----
           kcA = (kcB + 1 == KC) ? 0 : kcB + 1;
-          if (t + 2 < T) load_tile(c_cnt + 1, kcA, wA, xA);
+          if (t + 2 < T) { load_tile(kcA, wA, xA); stA = ld_st; }
           compute(wB, xB);
-          ++c_cnt;
+          release(stB);
+          if (dbg_on && op >= 20 && op < 24 && t + 1 < 60) a.dbg[(2 * nops_all + 2) * 4 + (op - 20) * 64 + t + 1] = globaltimer_ns();
           if (kcB == KC - 1) finish_group();
         }
       } else {
         // ---------------- epilogue warp: reduce the 8 partials per row in fixed order, fused epilogues ----------------
         // Operands the epilogue needs from global memory (residual pair for O/DOWN, RoPE cos/sin for QKV) are
-        // preloaded for ALL row pairs of this CTA at op start — lane i holds pair i — while the consumers are still in
-        // their prologue; per group they are redistributed with a shuffle.  (A dependent L2 load per group would
-        // throttle the whole CTA to one group per ~0.7 us through the mailbox back-pressure.)
-        const int npairs = gn * (TR / 2);
-        const bool pre_ok = npairs <= 32;
+        // preloaded for the row pairs of this CTA at op start — lane i holds pairs i and i+32 — while the consumers are
+        // still in their prologue; per group they are redistributed with a shuffle.  (A dependent L2 load per group
+        // would throttle the whole CTA to one group per ~0.7 us through the mailbox back-pressure.)
+        const bool pre_ok = pn <= 64;
         const int q_rows = a.Hq * a.hd, kv_rows = a.Hkv * a.hd;
-        float2 pre = make_float2(0.f, 0.f);
-        if (pre_ok && lane < npairs) {
-          const int np = g0 * TR + 2 * lane;
-          if (o.kind == OP_O || o.kind == OP_DOWN) {
-            const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(a.x + np);
-            pre = make_float2(__low2float(rv), __high2float(rv));
-          } else if (o.kind == OP_QKV && np < q_rows + kv_rows) {
-            pre = a.rope[(size_t)pos * (a.hd / 2) + ((np % a.hd) >> 1)];
+        float2 pre[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        if (pre_ok && (o.kind == OP_O || o.kind == OP_DOWN || o.kind == OP_QKV)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int pi = lane + 32 * h;
+            if (pi < pn) {
+              const int np = (p0 + pi) * 2;
+              if (o.kind != OP_QKV) {
+                const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(a.x + np);
+                pre[h] = make_float2(__low2float(rv), __high2float(rv));
+              } else if (np < q_rows + kv_rows) {
+                pre[h] = a.rope[(size_t)pos * (a.hd / 2) + ((np % a.hd) >> 1)];
+              }
+            }
           }
         }
-        for (int g = 0; g < gn; ++g) {
-          const float2 pg = make_float2(__shfl_sync(0xffffffffu, pre.x, (g * (TR / 2) + lane) & 31),
-                                        __shfl_sync(0xffffffffu, pre.y, (g * (TR / 2) + lane) & 31));
+        for (int g = 0; g < ngroups; ++g) {
+          const int pi = 4 * g + (lane & 3);                    // pair index inside the CTA handled by lanes 0..3
+          const float2 s0 = make_float2(__shfl_sync(0xffffffffu, pre[0].x, pi & 31), __shfl_sync(0xffffffffu, pre[0].y, pi & 31));
+          const float2 s1 = make_float2(__shfl_sync(0xffffffffu, pre[1].x, pi & 31), __shfl_sync(0xffffffffu, pre[1].y, pi & 31));
+          const float2 pg = (pi & 32) ? s1 : s0;
           const int ps = g_cnt % MK_NSLOT;
           mbar_wait(&done[ps], (g_cnt / MK_NSLOT) & 1u);
           float v0 = 0.f, v1 = 0.f;
-          const int prs = (2 * lane) / 4, pr0 = (2 * lane) % 4;     // lane p owns the row pair (2p, 2p+1) of the group
-          if (lane < TR / 2) {
+          if (lane < 4) {
+            const int prs = (2 * lane) / RPW, pr0 = (2 * lane) % RPW;     // row subset / row inside the subset of pair `lane`
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
-              const float2 pv = *reinterpret_cast<const float2*>(part + (ps * NCW + prs * CB + c) * 4 + pr0);
+              const float2 pv = *reinterpret_cast<const float2*>(part + (ps * NCW + prs * CB + c) * 8 + pr0);
               v0 += pv.x; v1 += pv.y;
             }
           }
           ++g_cnt;
           __syncwarp();
           if (lane == 0) mbar_arrive(&freeb[ps]);
-          if (lane < TR / 2) {
-            const int n = (g0 + g) * TR + 2 * lane;
+          if (lane < 4 && pi < pn) {
+            const int n = (p0 + pi) * 2;
             if (o.kind == OP_QKV) {
               // Linear out -> bf16; RoPE in fp32 with separate mul/mul/sub like eager torch -> bf16 (App. A.2, A.7)
               const float x0 = round_bf(v0), x1 = round_bf(v1);

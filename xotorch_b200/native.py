@@ -162,11 +162,11 @@ class NativeShard:
     check(self.lib.xotb200_set_cta_limit(self.h, int(max_ctas)))
 
   def debug_timeline(self, step: int, cta: int = 0, read: bool = False):
-    n = (4 * self.cfg.n_layers + 2) * 4 * 2
+    n = (4 * self.cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8
     if read:
       out = np.zeros(n, dtype=np.uint64)
       check(self.lib.xotb200_debug_timeline(self.h, int(step), int(cta), out.ctypes.data_as(C.c_void_p), n))
-      return out.reshape(-1, 4)
+      return out
     check(self.lib.xotb200_debug_timeline(self.h, int(step), int(cta), None, 0))
     return None
 
