@@ -164,7 +164,7 @@ static int prepare_mega(xotb200_engine* e) {
   const size_t attn_scratch = ((size_t)NCW * R * 2 + (size_t)NCW * R * c.head_dim) * 4;
   const size_t xbuf = align_up(std::max(kmax * 2, attn_scratch), 128);
   const size_t smem = (size_t)mk_nstage(tk) * mk_stage_bytes(tk) + xbuf + (size_t)(2 * mk_nstage(tk) + 2 * MK_NSLOT) * 8 +
-                      (size_t)MK_NSLOT * NCW * 8 * 4 + 128 + 128;
+                      (size_t)MK_NSLOT * NCW * 8 * 4 + 128 + 128 + (size_t)c.n_layers * sizeof(LayerDev);
   REQUIRE(smem <= SMEM_BUDGET, "shared memory %zu > %zu: activation width %zu too large for the ring", smem, SMEM_BUDGET, kmax);
   CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;

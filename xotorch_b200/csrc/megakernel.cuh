@@ -28,10 +28,12 @@ constexpr int W_PROD = 8;                 // TMA producer warp
 constexpr int W_EPI = 9;                  // epilogue warp (cross-warp reduction + fused epilogues)
 constexpr int MK_THREADS = 320;
 constexpr int CONS_THREADS = NCW * 32;    // 256
-constexpr int MK_ROWS = 8;                // weight rows per ring stage (4 RoPE / gate-up pairs)
 constexpr int MK_NSLOT = 4;               // partial-sum hand-off slots consumer warps -> epilogue warp
-__host__ __device__ constexpr int mk_stage_bytes(int tk) { return MK_ROWS * tk * 2; }
-__host__ __device__ constexpr int mk_nstage(int tk) { return tk >= 2048 ? 6 : 12; }   // ring depth: 192 KiB (Llama sizes) / 96 KiB (tiny)
+// ring stage = mk_rows(tk) weight rows (whole RoPE / gate-up pairs) x tk columns: 16 KiB x 12 stages (Llama sizes, measured
+// 1.4 % faster than 32 KiB x 6) or 8 KiB x 12 (tiny parity shapes)
+__host__ __device__ constexpr int mk_rows(int tk) { return tk >= 2048 ? 4 : 8; }
+__host__ __device__ constexpr int mk_stage_bytes(int tk) { return mk_rows(tk) * tk * 2; }
+__host__ __device__ constexpr int mk_nstage(int tk) { return 12; }
 
 
 __device__ __forceinline__ void bar_sync(int id, int count) {
@@ -82,7 +84,7 @@ struct OpInfo {
   int N, K, kind, li;
 };
 
-__device__ __forceinline__ OpInfo op_info(const MegaArgs& a, int op) {
+__device__ __forceinline__ OpInfo op_info(const MegaArgs& a, const LayerDev* layers, int op) {
   OpInfo o;
   if (op == 4 * a.nl) {
     o.W = a.lm_head; o.N = a.V; o.K = a.D; o.kind = OP_HEAD; o.li = a.nl;
@@ -90,7 +92,7 @@ __device__ __forceinline__ OpInfo op_info(const MegaArgs& a, int op) {
   }
   o.li = op >> 2;
   o.kind = op & 3;
-  const LayerDev& l = a.layers[o.li];
+  const LayerDev& l = layers[o.li];
   switch (o.kind) {
     case OP_QKV: o.W = l.wqkv; o.N = (a.Hq + 2 * a.Hkv) * a.hd; o.K = a.D; break;
     case OP_O: o.W = l.wo; o.N = a.D; o.K = a.Hq * a.hd; break;
@@ -172,8 +174,40 @@ __device__ __forceinline__ bool grid_barrier(const MegaArgs& a, unsigned int& ta
 // ------------------------------------------------------------------------------------------------------------
 // attention phase (consumer warps only): one (kv head, context split) item per CTA, 8 warps, 16-byte K/V loads (HD/8 lanes per position)
 // ------------------------------------------------------------------------------------------------------------
+// K/V registers of the first position each lane group handles; loaded BEFORE the grid barrier that closes the QKV op
+// when that position was written by an earlier step (only position ctx-1 is new), so the L2 latency overlaps the barrier.
+struct AttnPre {
+  uint4 k, v;
+  bool have;
+};
+
+template <int HD>
+__device__ __forceinline__ AttnPre attn_prefetch(const MegaArgs& a, const LayerDev& lw, int ctx) {
+  constexpr int LPP = HD / 8;
+  constexpr int PPW = 32 / LPP;
+  AttnPre pre;
+  pre.k = make_uint4(0, 0, 0, 0); pre.v = pre.k; pre.have = false;
+  const int nsplit = a.nsplit;
+  const int item = blockIdx.x;
+  if (item >= a.Hkv * nsplit) return pre;
+  const int g = item / nsplit, split = item - g * nsplit;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPP, li = lane % LPP;
+  const int chunk = (ctx + nsplit - 1) / nsplit;
+  const int t0 = split * chunk;
+  const int t1 = min(ctx, t0 + chunk);
+  const int t = t0 + warp * PPW + sub;
+  if (t < t1 && t < ctx - 1) {
+    pre.k = __ldcg(reinterpret_cast<const uint4*>(lw.k_cache + ((size_t)g * a.L + t) * HD + li * 8));
+    pre.v = __ldcg(reinterpret_cast<const uint4*>(lw.v_cache + ((size_t)g * a.L + t) * HD + li * 8));
+    pre.have = true;
+  }
+  return pre;
+}
+
 template <int HD, int R>
-__device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw, int ctx, float* scratch) {
+__device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw, int ctx, float* scratch, const AttnPre& pre,
+                                           unsigned long long* stamp) {
   constexpr int LPP = HD / 8;        // lanes per position
   constexpr int PPW = 32 / LPP;      // positions per warp load
   const int nsplit = a.nsplit;
@@ -189,7 +223,7 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
   float q[R][8], acc[R][8], m[R], l[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const uint4 qv = *reinterpret_cast<const uint4*>(a.q + (size_t)(g * R + r) * HD + li * 8);
+    const uint4 qv = __ldcg(reinterpret_cast<const uint4*>(a.q + (size_t)(g * R + r) * HD + li * 8));
     unpack8(qv, q[r]);
     m[r] = -INFINITY; l[r] = 0.f;
 #pragma unroll
@@ -199,8 +233,8 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
   const bf16* vb = lw.v_cache + (size_t)g * a.L * HD + li * 8;
   const int stride = NCW * PPW;
   int t = t0 + warp * PPW + sub;
-  uint4 kn = make_uint4(0, 0, 0, 0), vn = kn;
-  if (t < t1) {
+  uint4 kn = pre.k, vn = pre.v;
+  if (t < t1 && !pre.have) {
     kn = __ldcg(reinterpret_cast<const uint4*>(kb + (size_t)t * HD));
     vn = __ldcg(reinterpret_cast<const uint4*>(vb + (size_t)t * HD));
   }
@@ -232,6 +266,7 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
       }
     }
   }
+  if (stamp && threadIdx.x == 0) stamp[1] = globaltimer_ns();
   // merge the PPW lane groups of the warp (fixed order), then the 8 warps through shared memory
 #pragma unroll
   for (int o = 16; o >= LPP; o >>= 1) {
@@ -284,6 +319,7 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
       a.part_ml[(hr * nsplit + split) * 2 + 1] = Ls;
     }
   }
+  if (stamp && threadIdx.x == 0) stamp[2] = globaltimer_ns();
   // ticket: the last split CTA of this kv head merges all splits (fixed order) and writes bf16
   __shared__ int s_last;
   bar_sync(1, CONS_THREADS);
@@ -294,6 +330,7 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
     if (s_last) a.tickets[g] = 0;
   }
   bar_sync(1, CONS_THREADS);
+  if (stamp && threadIdx.x == 0) stamp[3] = globaltimer_ns();
   if (!s_last) return;
   __threadfence();
   for (int idx = threadIdx.x; idx < R * HD; idx += CONS_THREADS) {
@@ -331,6 +368,7 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
 template <int TK, int HD, int R>
 __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int MK_ROWS = mk_rows(TK);            // weight rows per ring stage
   constexpr int ROWB = TK * 2;                    // bytes per stage row
   constexpr int STAGE_BYTES = mk_stage_bytes(TK);
   constexpr int NSTAGE = mk_nstage(TK);
@@ -350,6 +388,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
   uint64_t* freeb = done + MK_NSLOT;
   float* part = reinterpret_cast<float*>(freeb + MK_NSLOT);   // [NSLOT][NCW][8]
   float* red = part + MK_NSLOT * NCW * 8;
+  LayerDev* s_layers = reinterpret_cast<LayerDev*>(red + 32);   // layer table copy: no L2 round trip per op
   __shared__ volatile int s_abort;
   __shared__ int s_tok;
 
@@ -360,6 +399,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
     for (int i = 0; i < MK_NSLOT; ++i) { mbar_init(&done[i], NCW); mbar_init(&freeb[i], 1); }
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < a.nl * (int)(sizeof(LayerDev) / 8); i += MK_THREADS)
+    reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(a.layers)[i];
   __syncthreads();   // the only CTA-wide barrier: roles diverge below and never meet on barrier 0 again
 
   auto op_enabled = [&](int op, int step) -> bool {
@@ -383,9 +424,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
         if (c.s >= a.n_steps) { c.end = true; return; }
         if (c.op >= nops_all) { c.op = 0; ++c.s; continue; }
         if (!op_enabled(c.op, c.s)) { ++c.op; continue; }
-        const OpInfo o = op_info(a, c.op);
+        const OpInfo o = op_info(a, s_layers, c.op);
         cta_pairs(o.N, c.p0, c.pn);
-        c.ng = (c.pn + 3) >> 2;
+        c.ng = (c.pn + MK_ROWS / 2 - 1) / (MK_ROWS / 2);
         if (c.ng == 0) { ++c.op; continue; }
         c.W = o.W; c.K = o.K; c.N = o.N; c.KC = o.K / TK;
         return;
@@ -407,8 +448,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
       }
       if (aborted) break;
       uint8_t* dst = ring + (size_t)st * STAGE_BYTES;
-      const size_t row0 = (size_t)(ld.p0 + 4 * ld.g) * 2;
-      const int nrows = min(MK_ROWS, 2 * (ld.pn - 4 * ld.g));
+      const size_t row0 = (size_t)(ld.p0 + (MK_ROWS / 2) * ld.g) * 2;
+      const int nrows = min(MK_ROWS, 2 * (ld.pn - (MK_ROWS / 2) * ld.g));
       // K-panel layout [K/TK][N][TK]: the nrows x TK stage is contiguous in HBM -> ONE bulk copy of up to 32 KiB
       mbar_expect_tx(&full[st], (uint32_t)nrows * TK * 2);
       bulk_g2s(dst, ld.W + ((size_t)ld.kc * ld.N + row0) * TK, (uint32_t)nrows * TK * 2, &full[st], policy);
@@ -465,12 +506,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
     const bool dbg_on = a.dbg && s == a.dbg_step && (int)blockIdx.x == a.dbg_cta && threadIdx.x == 0;
 
     for (int op = 0; op < nops && ok; ++op) {
-      const OpInfo o = op_info(a, op);
-      const LayerDev* lw = o.kind == OP_HEAD ? nullptr : &a.layers[o.li];
+      const OpInfo o = op_info(a, s_layers, op);
+      const LayerDev* lw = o.kind == OP_HEAD ? nullptr : &s_layers[o.li];
       const int K = o.K, KC = K / TK;
       int p0, pn;
       cta_pairs(o.N, p0, pn);
-      const int ngroups = (pn + 3) >> 2;
+      const int ngroups = (pn + MK_ROWS / 2 - 1) / (MK_ROWS / 2);
       if (dbg_on) a.dbg[op * 4 + 0] = globaltimer_ns();
 
       if (!is_epi) {
@@ -619,14 +660,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
           }
         }
         for (int g = 0; g < ngroups; ++g) {
-          const int pi = 4 * g + (lane & 3);                    // pair index inside the CTA handled by lanes 0..3
+          const int pi = (MK_ROWS / 2) * g + (lane & 3);        // pair index inside the CTA handled by lanes 0..MK_ROWS/2-1
           const float2 s0 = make_float2(__shfl_sync(0xffffffffu, pre[0].x, pi & 31), __shfl_sync(0xffffffffu, pre[0].y, pi & 31));
           const float2 s1 = make_float2(__shfl_sync(0xffffffffu, pre[1].x, pi & 31), __shfl_sync(0xffffffffu, pre[1].y, pi & 31));
           const float2 pg = (pi & 32) ? s1 : s0;
           const int ps = g_cnt % MK_NSLOT;
           mbar_wait(&done[ps], (g_cnt / MK_NSLOT) & 1u);
           float v0 = 0.f, v1 = 0.f;
-          if (lane < 4) {
+          if (lane < MK_ROWS / 2) {
             const int prs = (2 * lane) / RPW, pr0 = (2 * lane) % RPW;     // row subset / row inside the subset of pair `lane`
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
@@ -637,7 +678,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
           ++g_cnt;
           __syncwarp();
           if (lane == 0) mbar_arrive(&freeb[ps]);
-          if (lane < 4 && pi < pn) {
+          if (lane < MK_ROWS / 2 && pi < pn) {
             const int n = (p0 + pi) * 2;
             if (o.kind == OP_QKV) {
               // Linear out -> bf16; RoPE in fp32 with separate mul/mul/sub like eager torch -> bf16 (App. A.2, A.7)
@@ -705,12 +746,19 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
       if (dbg_on) a.dbg[op * 4 + 2] = globaltimer_ns();
       // ---------------- op boundary ----------------
       const bool hop_out = (o.kind == OP_DOWN && o.li == a.nl - 1 && !a.last && a.mode == 0);
+      AttnPre apre;
+      apre.have = false;
+      if (o.kind == OP_QKV && !is_epi) apre = attn_prefetch<HD>(a, *lw, pos + 1);   // old K/V: overlap the barrier
       ok = grid_barrier(a, bar_target, &s_abort);
       if (!ok) break;
       if (o.kind == OP_QKV) {
-        if (!is_epi) attn_phase<HD, R>(a, *lw, pos + 1, reinterpret_cast<float*>(xbuf));
+        unsigned long long* stamp = (dbg_on && op == 20) ? a.dbg + (2 * nops_all + 2) * 4 + 48 : nullptr;
+        if (stamp) stamp[0] = globaltimer_ns();
+        if (!is_epi) attn_phase<HD, R>(a, *lw, pos + 1, reinterpret_cast<float*>(xbuf), apre, stamp);
+        if (stamp) stamp[4] = globaltimer_ns();
         ok = grid_barrier(a, bar_target, &s_abort);
         if (!ok) break;
+        if (stamp) stamp[5] = globaltimer_ns();
       }
       if (dbg_on) a.dbg[op * 4 + 3] = globaltimer_ns();
       // ---------------- publish (CTA 0, after the barrier that closes the producing op) ----------------
