@@ -223,54 +223,21 @@ def run_b200(args):
   D, V = shape.dim, shape.vocab
 
   # ---- link the ring: every engine learns the inbox of the next one (CUDA IPC across processes) ----
-  if n == 1:
-    eng.link_next_local(eng)
-  else:
-    handles = [None] * n
-    dist.all_gather_object(handles, eng.inbox_export())
-    eng.link_next_ipc(handles[next_r])
-    dist.barrier()
-
+  from xotorch_b200.ring import DistributedRing
   prompt = synth_prompt(V, N_PROMPT)
   max_len = N_PROMPT + N_GEN + 1
   dev = torch.device("cuda", local)
-
-  def hop_send(arr: np.ndarray):          # prefill / API-path hop: host ndarray -> next rank (NCCL send of the fp32 payload)
-    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev)
-    dist.send(t, next_r)
-
-  def hop_recv(shape_):
-    t = torch.empty(shape_, dtype=torch.float32, device=dev)
-    dist.recv(t, prev_r)
-    return t.cpu().numpy()
+  ring = DistributedRing(eng, rank, n, D, V, comm_device=dev)
+  ring.link()
 
   def prefill():
     """128-token prefill through the host-buffer API; hidden state handed over per shard (bytes = 2*S*D algorithmic)."""
-    eng.begin_request(max_len)
-    if n == 1:
-      return eng.forward(prompt, 0)
-    if first:
-      h = eng.forward(prompt, 0); hop_send(h); return None
-    h = hop_recv((1, N_PROMPT, D))
-    out = eng.forward(h, 0)
-    if not last:
-      hop_send(out); return None
-    return out
-
-  step_ctr = [0]
+    return ring.prefill(prompt, max_len)
 
   def ring_decode(n_steps: int):
-    """device-resident ring: last shard seeds shard 0 with the first generated token, then n_steps graph replays/rank."""
-    s0 = step_ctr[0]
-    if last:
-      eng.post_to_next(s0)
-    if n > 1:
-      dist.barrier()
+    """device-resident ring: last shard seeds shard 0 with the first generated token, then ONE persistent kernel/rank."""
     torch.cuda.synchronize()
-    eng.ring_launch(n_steps, s0, N_PROMPT)
-    toks, ms = eng.ring_wait(n_steps)
-    step_ctr[0] += n_steps
-    return toks, ms
+    return ring.ring_decode(n_steps, N_PROMPT)
 
   def barrier():
     if n > 1:
@@ -324,35 +291,12 @@ def run_b200(args):
   # ---- e2e: host-buffer API per token (H2D ids/hidden in, D2H logits/hidden out, every step) ----
   def api_request():
     prefill_out = prefill()
-    pos = N_PROMPT
     tok = int(np.argmax(prefill_out[0])) if last else 0
     if n > 1:
-      tt = torch.tensor([tok], dtype=torch.int64, device=dev)
-      dist.broadcast(tt, n - 1)
-      tok = int(tt.item())
+      tok = ring._bcast_token(tok)
     barrier()
     t0 = time.perf_counter()
-    out_ids = []
-    for i in range(N_GEN):
-      if n == 1:
-        logits = eng.forward(np.array([[tok]], dtype=np.int32), pos)
-        tok = int(np.argmax(logits[0]))
-      else:
-        if first:
-          h = eng.forward(np.array([[tok]], dtype=np.int32), pos)
-          hop_send(h)
-        else:
-          h = hop_recv((1, 1, D))
-          o = eng.forward(h, pos)
-          if not last:
-            hop_send(o)
-          else:
-            tok = int(np.argmax(o[0]))
-        tt = torch.tensor([tok], dtype=torch.int64, device=dev)
-        dist.broadcast(tt, n - 1)               # ring closure: token id back to shard 0 (4-byte payload)
-        tok = int(tt.item())
-      out_ids.append(tok)
-      pos += 1
+    out_ids = ring.api_decode(tok, N_PROMPT, N_GEN)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0), out_ids
 

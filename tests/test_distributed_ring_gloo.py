@@ -1,0 +1,105 @@
+"""N>1 host logic on CPU: world_size-2 and -3 `gloo` process groups drive `DistributedRing` with a stand-in for the CUDA
+library (no compute is claimed; the device ring itself is covered on GPUs by tests/test_gpu_parity.py and bench.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from xotorch_b200.ring import DistributedRing
+from xotorch_b200.topology.partitioning import Partition, map_partitions_to_shards
+
+D, V, NL = 16, 64, 6
+
+
+class FakeShard:
+  """Deterministic stand-in with the NativeShard surface DistributedRing uses."""
+
+  def __init__(self, rank, start, end):
+    self.rank, self.start, self.end = rank, start, end
+    self.linked, self.calls = None, []
+
+  @property
+  def is_first(self): return self.start == 0
+  @property
+  def is_last(self): return self.end == NL - 1
+
+  def inbox_export(self): return bytes([self.rank]) * 64
+  def link_next_ipc(self, h): self.linked = h[0]
+  def link_next_local(self, other): self.linked = "self"
+  def begin_request(self, n): self.calls.append(("begin", n))
+
+  def forward(self, x, pos0):
+    self.calls.append(("forward", x.ndim, tuple(x.shape), pos0))
+    if x.ndim == 2:
+      h = np.zeros((1, x.shape[1], D), np.float32) + x[0][:, None].astype(np.float32)
+    else:
+      h = x.astype(np.float32)
+    h = h + np.float32(self.end - self.start + 1)          # every layer adds 1
+    if self.is_last:
+      logits = np.zeros((1, V), np.float32)
+      logits[0, int(h[0, -1, 0] + pos0) % V] = 1.0
+      return logits
+    return h
+
+
+def _shards(world):
+  parts, start = [], 0.0
+  for i in range(world):
+    end = round(start + 1.0 / world, 5)
+    parts.append(Partition(str(i), start, end))
+    start = end
+  return map_partitions_to_shards(parts, NL, "m")
+
+
+def _worker(rank, world, port, q):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  sh = _shards(world)[rank]
+  native = FakeShard(rank, sh.start_layer, sh.end_layer)
+  ring = DistributedRing(native, rank, world, D, V, comm_device="cpu")
+  ring.link()
+  prompt = np.arange(5, dtype=np.int32).reshape(1, -1)
+  logits = ring.prefill(prompt, 5 + 8 + 1)
+  tok = int(np.argmax(logits[0])) if native.is_last else 0
+  tok = ring._bcast_token(tok)
+  ids = ring.api_decode(tok, 5, 8)
+  q.put((rank, native.linked, tok, ids, native.calls))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def _free_port():
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_ring_host_logic(world):
+  # single-process truth: one shard covering all layers
+  one = FakeShard(0, 0, NL - 1)
+  ring1 = DistributedRing(one, 0, 1, D, V)
+  ring1.link()
+  prompt = np.arange(5, dtype=np.int32).reshape(1, -1)
+  tok1 = int(np.argmax(ring1.prefill(prompt, 14)[0]))
+  ids1 = ring1.api_decode(tok1, 5, 8)
+  assert one.linked == "self"
+
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs: p.start()
+  res = sorted(q.get(timeout=120) for _ in range(world))
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  for rank, linked, tok, ids, calls in res:
+    assert linked == (rank + 1) % world                 # each rank mapped the inbox of the NEXT rank
+    assert tok == tok1 and ids == ids1                  # sharded ring == unsharded, on every rank
+    fw = [c for c in calls if c[0] == "forward"]
+    assert len(fw) == 9 and fw[0][3] == 0 and [c[3] for c in fw[1:]] == list(range(5, 13))
+    assert fw[0][1] == (2 if rank == 0 else 3)          # ndim protocol: ids on the first shard, hidden elsewhere
+    assert calls[0] == ("begin", 14)

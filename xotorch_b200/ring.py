@@ -55,3 +55,99 @@ class LocalRing:
       ms = max(ms, m)
     self._step += n_gen - 1
     return np.concatenate([[first], toks]).astype(np.int32), ms
+
+
+class DistributedRing:
+  """One process per shard (torchrun / torch.distributed): rank r owns shard r of the ring and GPU LOCAL_RANK.
+
+  `torch.distributed` is plumbing only: it carries the CUDA-IPC inbox handles at link time, the fp32 hidden state of
+  the HOST-API path (prefill and the per-token e2e path; bytes = 4*S*D per hop) and the 4-byte token id that closes the
+  ring on that path.  The device-resident decode (`ring_decode`) uses no collective at all: activations and tokens move
+  between the engines' inboxes by peer stores + flags inside the persistent kernel.
+
+  Mirrors what the reference's Node does per request across peers (node.py:193-208 prefill on the first shard, :361-380
+  process_tensor on the others, :424-443 forward to partition (i+1) % n, :109-147 sample on the last shard)."""
+
+  def __init__(self, native, rank: int, world: int, dim: int, vocab: int, comm_device="cpu"):
+    import torch.distributed as dist
+    self.dist, self.native, self.rank, self.world = dist, native, rank, world
+    self.dim, self.vocab = dim, vocab
+    self.prev, self.next = (rank - 1) % world, (rank + 1) % world
+    self.comm_device = comm_device
+    self.first, self.last = native.is_first, native.is_last
+    self.step = 0                      # monotonic ring step counter, identical on every rank
+
+  # -- link: every engine learns the inbox of the next one -----------------------------------------------------------
+  def link(self):
+    if self.world == 1:
+      self.native.link_next_local(self.native)
+      return
+    handles = [None] * self.world
+    self.dist.all_gather_object(handles, self.native.inbox_export())
+    self.native.link_next_ipc(handles[self.next])
+    self.dist.barrier()
+
+  # -- host-array hop (API-compatible path) -----------------------------------------------------------------------------
+  def _send(self, arr: np.ndarray):
+    import torch
+    self.dist.send(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.comm_device), self.next)
+
+  def _recv(self, shape) -> np.ndarray:
+    import torch
+    t = torch.empty(shape, dtype=torch.float32, device=self.comm_device)
+    self.dist.recv(t, self.prev)
+    return t.cpu().numpy()
+
+  def _bcast_token(self, tok: int) -> int:
+    import torch
+    t = torch.tensor([tok], dtype=torch.int64, device=self.comm_device)
+    self.dist.broadcast(t, self.world - 1)
+    return int(t.item())
+
+  def forward_through_ring(self, ids_or_none: Optional[np.ndarray], n_tokens: int, pos0: int) -> Optional[np.ndarray]:
+    """One pass of `n_tokens` positions through all shards with host buffers.  Rank 0 passes the ids; the last rank
+    returns the logits [1, V]; every other rank returns None."""
+    if self.world == 1:
+      return self.native.forward(ids_or_none, pos0)
+    if self.first:
+      self._send(self.native.forward(ids_or_none, pos0))
+      return None
+    h = self._recv((1, n_tokens, self.dim))
+    out = self.native.forward(h, pos0)
+    if not self.last:
+      self._send(out)
+      return None
+    return out
+
+  def prefill(self, prompt_ids: np.ndarray, max_total_len: int) -> Optional[np.ndarray]:
+    self.native.begin_request(max_total_len)
+    ids = np.asarray(prompt_ids, dtype=np.int32).reshape(1, -1)
+    return self.forward_through_ring(ids if self.first else None, ids.shape[1], 0)
+
+  def api_decode(self, first_token: int, pos0: int, n_gen: int) -> List[int]:
+    """Greedy decode through the host API, token by token (what Node drives): returns the n_gen ids on every rank."""
+    tok, pos, out = first_token, pos0, []
+    for _ in range(n_gen):
+      ids = np.array([[tok]], dtype=np.int32)
+      logits = self.forward_through_ring(ids if self.first else None, 1, pos)
+      if self.last:
+        tok = int(np.argmax(logits[0]))
+      if self.world > 1:
+        tok = self._bcast_token(tok)            # ring closure: the id travels back to the first shard
+      out.append(tok)
+      pos += 1
+    return out
+
+  # -- device-resident decode -------------------------------------------------------------------------------------------
+  def ring_decode(self, n_steps: int, pos0: int) -> Tuple[Optional[np.ndarray], float]:
+    """After a prefill: the last shard seeds shard 0's inbox with the first generated token, then every rank launches
+    ONE persistent kernel for n_steps tokens.  Returns (ids on the last rank | None, device ms of this rank)."""
+    s0 = self.step
+    if self.last:
+      self.native.post_to_next(s0)
+    if self.world > 1:
+      self.dist.barrier()
+    self.native.ring_launch(n_steps, s0, pos0)
+    toks, ms = self.native.ring_wait(n_steps)
+    self.step += n_steps
+    return toks, ms
