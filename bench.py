@@ -126,47 +126,48 @@ def even_partition(n_layers: int, n: int, rank: int):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline (oracle = test infrastructure; only place bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(sample_layers: int = 2, decode_steps: int = 8, repeats: int = 1):
+def cpu_reference_sample(sample_layers: int = 4, decode_steps: int = 8):
   """Bounded sample of the SAME workload on the host cores: the 8B-shaped model cut to `sample_layers` layers + the
-  full embedding/lm_head rows it touches, 128-token prefill then `decode_steps` greedy steps; per-token time is
-  extrapolated to 32 layers (t_layer*32 + t_head).  Returns tokens/s and a description."""
+  full lm_head, 128-token prefill then `decode_steps` greedy steps (median step time); the final-norm + lm_head +
+  sampler cost is timed separately in the same process, so  t_layer = (t_step - t_head) / sample_layers  and the
+  per-token time is extrapolated as  t_layer * 32 + t_head.  Returns (tokens/s, cores, description)."""
+  import dataclasses
   import torch
-  from oracle.ref_engine import RefEngine, RefShard, model_config_from_hf
+  import torch.nn.functional as F
+  from oracle.ref_engine import RefEngine, RefShard, model_config_from_hf, rms_norm
   from oracle.synth_fast import synth_state_dict_fast
   from xotorch_b200.synth import PRESETS, hf_config, synth_prompt
-  import dataclasses
   shape = PRESETS[MODEL]
   cores = usable_cores()
   torch.set_num_threads(cores)
   sd = synth_state_dict_fast(shape, SEED, layers=range(sample_layers))
   prompt = synth_prompt(shape.vocab, N_PROMPT)
-
-  def run(n_layers):
-    sub = dataclasses.replace(shape, n_layers=n_layers)
-    cfg = model_config_from_hf(hf_config(sub))
-    eng = RefEngine(cfg, sd, RefShard(MODEL, 0, n_layers - 1, n_layers))
-    x, state = prompt.astype(np.int32), None
-    logits, state = eng.infer_tensor("cpu", eng.shard, x, state)           # prefill (untimed)
-    tok = eng.sample(logits, temp=0.0)
+  sub = dataclasses.replace(shape, n_layers=sample_layers)
+  cfg = model_config_from_hf(hf_config(sub))
+  eng = RefEngine(cfg, sd, RefShard(MODEL, 0, sample_layers - 1, sample_layers))
+  logits, state = eng.infer_tensor("cpu", eng.shard, prompt.astype(np.int32), None)      # prefill (untimed)
+  tok = eng.sample(logits, temp=0.0)
+  steps = []
+  for _ in range(decode_steps):
     t0 = time.perf_counter()
-    for _ in range(decode_steps):
-      logits, state = eng.infer_tensor("cpu", eng.shard, tok.astype(np.int32).reshape(1, 1), state)
-      tok = eng.sample(logits, temp=0.0)                                   # reference sampler at temp 0 (node.py:121)
-    return (time.perf_counter() - t0) / decode_steps
-
-  best = None
-  for _ in range(repeats):
-    t_a = run(sample_layers)                 # sample_layers layers + head
-    t_b = run(max(1, sample_layers // 2))    # half the layers + head  -> separates per-layer from head cost
-    la, lb = sample_layers, max(1, sample_layers // 2)
-    t_layer = (t_a - t_b) / (la - lb) if la != lb else t_a / la
-    t_head = max(t_a - la * t_layer, 0.0)
-    t_tok = t_layer * shape.n_layers + t_head
-    best = t_tok if best is None else min(best, t_tok)
-  desc = (f"oracle RefEngine (bf16 CPU, full-L masked SDPA, GQA expand, reference sampler temp 0), {MODEL} shape cut to "
-          f"{sample_layers} and {max(1, sample_layers // 2)} layers + lm_head, 128-token prefill then {decode_steps} decode steps; "
-          f"per-token time extrapolated to {shape.n_layers} layers")
-  return 1.0 / best, cores, desc
+    logits, state = eng.infer_tensor("cpu", eng.shard, tok.astype(np.int32).reshape(1, 1), state)
+    tok = eng.sample(logits, temp=0.0)                                     # reference sampler at temp 0 (node.py:121)
+    steps.append(time.perf_counter() - t0)
+  heads = []
+  h = torch.randn(1, 1, shape.dim).to(torch.bfloat16)
+  for _ in range(decode_steps):
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+      lg = F.linear(rms_norm(h, eng.model.norm, cfg["norm_eps"]), eng.model.output)[:, -1].float().numpy()
+    eng.sample(lg, temp=0.0)
+    heads.append(time.perf_counter() - t0)
+  t_step, t_head = float(np.median(steps)), float(np.median(heads))
+  t_layer = max(t_step - t_head, 0.0) / sample_layers
+  t_tok = t_layer * shape.n_layers + t_head
+  desc = (f"oracle RefEngine (bf16 CPU, KV prompt+1024, full-L masked SDPA, GQA expand, reference sampler temp 0), {MODEL} shape "
+          f"cut to {sample_layers} layers + lm_head, 128-token prefill then {decode_steps} decode steps (median {t_step * 1e3:.0f} ms/step, "
+          f"head alone {t_head * 1e3:.0f} ms); per-token time = t_layer*{shape.n_layers} + t_head")
+  return 1.0 / t_tok, cores, desc
 
 
 def run_reference(args):
@@ -176,7 +177,7 @@ def run_reference(args):
   t0 = time.time()
   vals = []
   for _ in range(max(1, min(args.steps, 2))):
-    v, cores, desc = cpu_reference_sample(sample_layers=2, decode_steps=8)
+    v, cores, desc = cpu_reference_sample(sample_layers=4, decode_steps=8)
     vals.append(v)
   v = float(np.mean(vals))
   line = {
@@ -337,7 +338,7 @@ def run_b200(args):
     cpu = None
     if n == 1 and not args.no_cpu_baseline:
       try:
-        v, cores, desc = cpu_reference_sample(sample_layers=2, decode_steps=8)
+        v, cores, desc = cpu_reference_sample(sample_layers=4, decode_steps=8)
         cpu = {"value": round(v, 4), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc}
       except Exception as ex:  # the CPU leg must never take the GPU number down with it
         cpu = {"value": None, "unit": "tokens/s", "cores": usable_cores(), "kind": "port", "sample": f"failed: {ex!r}"}
