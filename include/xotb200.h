@@ -125,6 +125,12 @@ int xotb200_ring_timestamps(xotb200_engine* e, uint64_t* t_in, uint64_t* t_out, 
  * Limit the persistent kernel to max_ctas CTAs (0 = one per SM).  Needed when several engines share ONE GPU and run
  * ring mode concurrently: their persistent kernels must be co-resident (sum of limits <= SM count). */
 int xotb200_set_cta_limit(xotb200_engine* e, int max_ctas);
+/* Prefill path: 0 = automatic (>= 8 positions per call run as tensor-core GEMMs: tcgen05 + TMEM + TMA tensor maps,
+ * prefill_tc.cuh; fewer run through the decode kernel), 1 = always the decode kernel, 2 = always tensor cores. */
+int xotb200_set_prefill_mode(xotb200_engine* e, int mode);
+/* Unit-test hook for the tensor-core GEMM: out[S,N] (bf16 bits) = A[S,K] * W[N,K]^T with fp32 accumulation, W re-laid out
+ * as K-panels of width tk exactly like a model weight.  S <= 128. */
+int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16, int S, int N, int K, int tk, void* out_bf16);
 /* Per-op device timeline of CTA `cta` at ring step `step` (-1 disables): for op i the four globaltimer stamps
  * [prologue start, tiles start, tiles done, barrier exit] at out[4*i..4*i+3].  Call once to arm (out may be NULL),
  * run the ring, call again to read. */

@@ -56,6 +56,8 @@ _SIGS = {
   "xotb200_ring_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
   "xotb200_ring_timestamps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
   "xotb200_set_cta_limit": (C.c_int, [C.c_void_p, C.c_int]),
+  "xotb200_set_prefill_mode": (C.c_int, [C.c_void_p, C.c_int]),
+  "xotb200_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
   "xotb200_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
   "xotb200_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
   "xotb200_weight_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

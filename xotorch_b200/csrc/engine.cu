@@ -31,6 +31,7 @@
 #include "../../include/xotb200.h"
 #include "kernels.cuh"
 #include "megakernel.cuh"
+#include "prefill_tc.cuh"
 
 using namespace xb;
 
@@ -117,6 +118,12 @@ struct xotb200_engine {
   size_t mega_smem = 0;
   int mega_xbuf = 0, mega_grid = 0;
   int cta_limit = 0;
+  // tensor-core prefill (prefill_tc.cuh)
+  int prefill_mode = 0;            // 0 auto (TC when n_tokens >= 8), 1 always the decode kernel, 2 always TC
+  bf16 *tc_x = nullptr, *tc_xn = nullptr, *tc_qkv = nullptr, *tc_q = nullptr, *tc_ao = nullptr, *tc_gu = nullptr, *tc_act = nullptr;
+  CUtensorMap tm_xn, tm_ao, tm_act;
+  std::vector<CUtensorMap> tm_w;   // 4 per local layer (qkv, o, gu, down) + head
+  bool tc_ready = false;
   unsigned long long* dbg = nullptr;
   int dbg_step = -1, dbg_cta = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -207,6 +214,187 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// tensor-core prefill: tensor maps, scratch, driver
+// --------------------------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  }
+  return fn;
+}
+// activations [128, K] row-major bf16 -> box {64 k, 128 rows}, SWIZZLE_128B
+static int make_tmap_act(CUtensorMap* m, bf16* ptr, int K) {
+  encode_tiled_fn enc = get_encode_tiled();
+  REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)TC_M};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_M};
+  const cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation K=%d) failed: %d", K, (int)r);
+  return 0;
+}
+// weights in K-panel layout [K/tk][N][tk] -> 3-D map {tk, N, K/tk}, box {64 k, nt rows, 1}, SWIZZLE_128B
+static int make_tmap_w(CUtensorMap* m, const bf16* ptr, int N, int K, int tk, int nt) {
+  encode_tiled_fn enc = get_encode_tiled();
+  REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)tk, (cuuint64_t)N, (cuuint64_t)(K / tk)};
+  const cuuint64_t strides[2] = {(cuuint64_t)tk * 2, (cuuint64_t)N * tk * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)nt, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights N=%d K=%d tk=%d) failed: %d", N, K, tk, (int)r);
+  return 0;
+}
+static int tc_nt(int N) { return N <= 8192 ? 32 : 128; }
+
+template <int NT>
+static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
+                             cudaStream_t st) {
+  void (*fn)(CUtensorMap, CUtensorMap, TcGemmArgs) = nullptr;
+  switch (epi) {
+    case TCE_STORE: fn = tc_gemm_kernel<NT, TCE_STORE>; break;
+    case TCE_RESID: fn = tc_gemm_kernel<NT, TCE_RESID>; break;
+    default: fn = tc_gemm_kernel<NT, TCE_HEAD_LAST>; break;
+  }
+  static std::map<std::pair<int, void*>, bool> attr_done;
+  auto key = std::make_pair(e->device, (void*)fn);
+  if (!attr_done.count(key)) {
+    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT)));
+    attr_done[key] = true;
+  }
+  fn<<<a.N / NT, TC_THREADS, tc_smem_bytes(NT), st>>>(tmA, tmB, a);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
+                          cudaStream_t st) {
+  const int nt = tc_nt(a.N);
+  REQUIRE(a.N % nt == 0 && a.K % TC_BK == 0, "tensor-core GEMM needs N %% %d == 0 and K %% 64 == 0 (N=%d K=%d)", nt, a.N, a.K);
+  return nt == 32 ? launch_tc_gemm_nt<32>(e, tmA, tmB, a, epi, st) : launch_tc_gemm_nt<128>(e, tmA, tmB, a, epi, st);
+}
+
+static int prepare_tc(xotb200_engine* e) {
+  if (e->tc_ready) return 0;
+  const xotb200_model_cfg& c = e->cfg;
+  const size_t D = c.dim, F = c.ffn, qd = (size_t)c.n_heads * c.head_dim, nqkv = (size_t)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  if (!e->tc_x) {
+    CK(cudaMalloc(&e->tc_x, TC_M * D * 2));
+    CK(cudaMalloc(&e->tc_xn, TC_M * D * 2));
+    CK(cudaMalloc(&e->tc_qkv, TC_M * nqkv * 2));
+    CK(cudaMalloc(&e->tc_q, TC_M * qd * 2));
+    CK(cudaMalloc(&e->tc_ao, TC_M * qd * 2));
+    CK(cudaMalloc(&e->tc_gu, TC_M * 2 * F * 2));
+    CK(cudaMalloc(&e->tc_act, TC_M * F * 2));
+    CK(cudaMemset(e->tc_xn, 0, TC_M * D * 2));
+    CK(cudaMemset(e->tc_ao, 0, TC_M * qd * 2));
+    CK(cudaMemset(e->tc_act, 0, TC_M * F * 2));
+    if (int rc = make_tmap_act(&e->tm_xn, e->tc_xn, (int)D)) return rc;
+    if (int rc = make_tmap_act(&e->tm_ao, e->tc_ao, (int)qd)) return rc;
+    if (int rc = make_tmap_act(&e->tm_act, e->tc_act, (int)F)) return rc;
+  }
+  const int nl = e->end - e->start + 1;
+  e->tm_w.assign((size_t)4 * nl + 1, CUtensorMap{});
+  for (int li = 0; li < nl; ++li) {
+    const LayerW& w = e->layers[li];
+    if (int rc = make_tmap_w(&e->tm_w[4 * li + 0], w.wqkv, (int)nqkv, (int)D, e->tk, tc_nt((int)nqkv))) return rc;
+    if (int rc = make_tmap_w(&e->tm_w[4 * li + 1], w.wo, (int)D, (int)qd, e->tk, tc_nt((int)D))) return rc;
+    if (int rc = make_tmap_w(&e->tm_w[4 * li + 2], w.wgu, (int)(2 * F), (int)D, e->tk, tc_nt((int)(2 * F)))) return rc;
+    if (int rc = make_tmap_w(&e->tm_w[4 * li + 3], w.wdown, (int)D, (int)F, e->tk, tc_nt((int)D))) return rc;
+  }
+  if (e->last)
+    if (int rc = make_tmap_w(&e->tm_w[4 * nl], e->lm_head, c.vocab, (int)D, e->tk, tc_nt(c.vocab))) return rc;
+  e->tc_ready = true;
+  return 0;
+}
+
+template <int HD>
+static int launch_tc_attn(xotb200_engine* e, int S, int R, bf16* kc, bf16* vc, int pos0, cudaStream_t st) {
+  dim3 grid(S, e->cfg.n_kv_heads);
+  const float scale = 1.0f / sqrtf((float)HD);
+  switch (R) {
+    case 2: tc_attn_prefill_kernel<HD, 2><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale); break;
+    case 4: tc_attn_prefill_kernel<HD, 4><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale); break;
+    case 8: tc_attn_prefill_kernel<HD, 8><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale); break;
+    default: set_err("unsupported GQA ratio %d", R); return XOTB200_EINVAL;
+  }
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+// Prefill n_tokens positions starting at pos0 on the tensor cores, in tiles of 128 tokens.  Inputs: stage_tokens /
+// stage_in; outputs: stage_out (non-last shard) or logits + ctl->token of the last position (last shard).
+static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st) {
+  if (int rc = prepare_tc(e)) return rc;
+  const xotb200_model_cfg& c = e->cfg;
+  const int D = c.dim, F = c.ffn, Hq = c.n_heads, Hkv = c.n_kv_heads, hd = c.head_dim;
+  const int qd = Hq * hd, nqkv = (Hq + 2 * Hkv) * hd, nl = e->end - e->start + 1;
+  for (int m0 = 0; m0 < n_tokens; m0 += TC_M) {
+    const int S = std::min(TC_M, n_tokens - m0);
+    if (e->first) {
+      tc_gather_kernel<<<S, 128, 0, st>>>(e->stage_tokens + m0, e->embed, e->tc_x, D);
+      CK(cudaGetLastError());
+      e->launches++;
+    } else {
+      CK(cudaMemcpyAsync(e->tc_x, e->stage_in + (size_t)m0 * D, (size_t)S * D * 2, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int li = 0; li < nl; ++li) {
+      const LayerW& w = e->layers[li];
+      bf16* kc = e->kv + ((size_t)li * 2 + 0) * Hkv * e->L * hd;
+      bf16* vc = e->kv + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
+      tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.attn_norm, e->tc_xn, D, c.norm_eps);
+      CK(cudaGetLastError());
+      TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv};
+      if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 0], g, TCE_STORE, st)) return rc;
+      tc_rope_kv_kernel<<<S, 256, 0, st>>>(e->tc_qkv, e->tc_q, kc, vc, e->rope, Hq, Hkv, hd, e->L, pos0 + m0);
+      CK(cudaGetLastError());
+      if (int rc = (hd == 128 ? launch_tc_attn<128>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)
+                              : launch_tc_attn<64>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)))
+        return rc;
+      TcGemmArgs o{S, D, qd, e->tk, e->tc_x, nullptr, D};
+      if (int rc = launch_tc_gemm(e, e->tm_ao, e->tm_w[4 * li + 1], o, TCE_RESID, st)) return rc;
+      tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.mlp_norm, e->tc_xn, D, c.norm_eps);
+      CK(cudaGetLastError());
+      TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F};
+      if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 2], u, TCE_STORE, st)) return rc;
+      tc_swiglu_kernel<<<S, 256, 0, st>>>(e->tc_gu, e->tc_act, F);
+      CK(cudaGetLastError());
+      TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D};
+      if (int rc = launch_tc_gemm(e, e->tm_act, e->tm_w[4 * li + 3], d, TCE_RESID, st)) return rc;
+      e->launches += 4;
+    }
+    if (e->last) {
+      if (m0 + S == n_tokens) {   // logits of the last position only (sharded_inference_engine.py:365-368)
+        tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, e->final_norm, e->tc_xn, D, c.norm_eps);
+        CK(cudaGetLastError());
+        TcGemmArgs h{S, c.vocab, D, e->tk, nullptr, e->logits, 0};
+        if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * nl], h, TCE_HEAD_LAST, st)) return rc;
+        tc_argmax_kernel<<<1, 1024, 0, st>>>(e->logits, c.vocab, e->ctl);
+        CK(cudaGetLastError());
+        e->launches += 2;
+      }
+    } else {
+      CK(cudaMemcpyAsync(e->stage_out + (size_t)m0 * D, e->tc_x, (size_t)S * D * 2, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  // the residual stream of the last position is what xotb200_post_to_next hands to the next shard
+  CK(cudaMemcpyAsync(e->x, e->tc_x + (size_t)((n_tokens - 1) % TC_M) * D, (size_t)D * 2, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------
 // minimal JSON (safetensors header) parser
 // --------------------------------------------------------------------------------------------------------------
 struct StEntry {
@@ -288,6 +476,8 @@ static void free_shard(xotb200_engine* e) {
   e->layers.clear();
   e->slots.clear();
   e->mega = nullptr;
+  e->tm_w.clear();
+  e->tc_ready = false;
   e->embed = e->final_norm = e->lm_head = nullptr;
   e->start = e->end = -1;
   e->L = 0;
@@ -382,6 +572,9 @@ int xotb200_destroy(xotb200_engine* e) {
   cudaDeviceSynchronize();
   free_shard(e);
   if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
+  void* tcp[] = {e->tc_x, e->tc_xn, e->tc_qkv, e->tc_q, e->tc_ao, e->tc_gu, e->tc_act};
+  for (void* p : tcp)
+    if (p) cudaFree(p);
   void* ptrs[] = {e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
                   e->cta_best_idx, e->ctl, e->bar_counter, e->dbg, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
                   e->stage_f32, e->stage_in, e->stage_out};
@@ -654,7 +847,12 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
     CK(cudaGetLastError());
     e->launches++;
   }
-  if (int rc = launch_mega(e, 1, n_tokens, 0, pos0, st)) return rc;   // one launch walks all n_tokens positions
+  const bool use_tc = e->prefill_mode == 2 || (e->prefill_mode == 0 && n_tokens >= 8);
+  if (use_tc) {
+    if (int rc = prefill_tc(e, n_tokens, pos0, st)) return rc;     // GEMM-shaped: 5th-gen tensor cores
+  } else {
+    if (int rc = launch_mega(e, 1, n_tokens, 0, pos0, st)) return rc;   // one launch walks all n_tokens positions
+  }
   if (e->last) {
     CK(cudaMemcpyAsync(out_f32, e->logits, (size_t)e->cfg.vocab * 4, cudaMemcpyDeviceToHost, st));
   } else {
@@ -785,6 +983,41 @@ int xotb200_set_cta_limit(xotb200_engine* e, int max_ctas) {
   REQUIRE(max_ctas == 0 || max_ctas >= e->cfg.n_kv_heads, "cta limit must be 0 (off) or >= n_kv_heads");
   e->cta_limit = max_ctas;
   e->mega = nullptr;   // re-resolve grid / splits on the next launch
+  return 0;
+}
+
+int xotb200_set_prefill_mode(xotb200_engine* e, int mode) {
+  REQUIRE(e && mode >= 0 && mode <= 2, "prefill mode must be 0 (auto), 1 (decode kernel) or 2 (tensor cores)");
+  e->prefill_mode = mode;
+  return 0;
+}
+
+int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16, int S, int N, int K, int tk, void* out_bf16) {
+  REQUIRE(e && a_bf16 && w_bf16 && out_bf16, "null argument");
+  REQUIRE(S >= 1 && S <= TC_M && K % tk == 0 && tk % TC_BK == 0 && N % tc_nt(N) == 0, "bad GEMM shape S=%d N=%d K=%d tk=%d", S, N, K, tk);
+  CK(cudaSetDevice(e->device));
+  bf16 *dA = nullptr, *dW0 = nullptr, *dW = nullptr, *dO = nullptr;
+  CK(cudaMalloc(&dA, (size_t)TC_M * K * 2));
+  CK(cudaMalloc(&dW0, (size_t)N * K * 2));
+  CK(cudaMalloc(&dW, (size_t)N * K * 2));
+  CK(cudaMalloc(&dO, (size_t)TC_M * N * 2));
+  CK(cudaMemset(dA, 0, (size_t)TC_M * K * 2));
+  CK(cudaMemcpy(dA, a_bf16, (size_t)S * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW0, w_bf16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+  relayout_rows_kernel<<<N, 128, 0, e->stream>>>(dW0, dW, N, K, 0, e->cfg.head_dim, 1, 0, N, tk);
+  CK(cudaGetLastError());
+  CUtensorMap tA, tB;
+  int rc = make_tmap_act(&tA, dA, K);
+  if (!rc) rc = make_tmap_w(&tB, dW, N, K, tk, tc_nt(N));
+  if (!rc) {
+    TcGemmArgs g{S, N, K, tk, dO, nullptr, N};
+    rc = launch_tc_gemm(e, tA, tB, g, TCE_STORE, e->stream);
+  }
+  cudaError_t er = cudaStreamSynchronize(e->stream);
+  if (!rc && er == cudaSuccess) er = cudaMemcpy(out_bf16, dO, (size_t)S * N * 2, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dW0); cudaFree(dW); cudaFree(dO);
+  if (rc) return rc;
+  CK(er);
   return 0;
 }
 

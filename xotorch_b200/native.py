@@ -161,6 +161,19 @@ class NativeShard:
   def set_cta_limit(self, max_ctas: int):
     check(self.lib.xotb200_set_cta_limit(self.h, int(max_ctas)))
 
+  def set_prefill_mode(self, mode: int):
+    """0 auto, 1 decode kernel only, 2 tensor-core GEMM prefill only"""
+    check(self.lib.xotb200_set_prefill_mode(self.h, int(mode)))
+
+  def debug_gemm(self, a_bits: np.ndarray, w_bits: np.ndarray, tk: int) -> np.ndarray:
+    """bf16 bit patterns in (uint16): A [S,K], W [N,K] -> out [S,N] bf16 bits, through the tcgen05 GEMM"""
+    a = np.ascontiguousarray(a_bits, dtype=np.uint16); w = np.ascontiguousarray(w_bits, dtype=np.uint16)
+    S, K = a.shape; N = w.shape[0]
+    out = np.empty((S, N), dtype=np.uint16)
+    check(self.lib.xotb200_debug_gemm(self.h, a.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), S, N, K, int(tk),
+                                      out.ctypes.data_as(C.c_void_p)))
+    return out
+
   def debug_timeline(self, step: int, cta: int = 0, read: bool = False):
     n = (4 * self.cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8
     if read:
