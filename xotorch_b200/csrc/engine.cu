@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -256,7 +257,10 @@ static int make_tmap_w(CUtensorMap* m, const bf16* ptr, int N, int K, int tk, in
   REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights N=%d K=%d tk=%d) failed: %d", N, K, tk, (int)r);
   return 0;
 }
-static int tc_nt(int N) { return N <= 8192 ? 32 : 128; }
+static int tc_nt(int N) {
+  static int small = getenv("XOTB200_TC_NT_SMALL") ? atoi(getenv("XOTB200_TC_NT_SMALL")) : 64;   // tuning hook (32 | 64)
+  return N <= 8192 ? small : 128;
+}
 
 template <int NT>
 static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
@@ -282,7 +286,9 @@ static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUten
                           cudaStream_t st) {
   const int nt = tc_nt(a.N);
   REQUIRE(a.N % nt == 0 && a.K % TC_BK == 0, "tensor-core GEMM needs N %% %d == 0 and K %% 64 == 0 (N=%d K=%d)", nt, a.N, a.K);
-  return nt == 32 ? launch_tc_gemm_nt<32>(e, tmA, tmB, a, epi, st) : launch_tc_gemm_nt<128>(e, tmA, tmB, a, epi, st);
+  if (nt == 32) return launch_tc_gemm_nt<32>(e, tmA, tmB, a, epi, st);
+  if (nt == 64) return launch_tc_gemm_nt<64>(e, tmA, tmB, a, epi, st);
+  return launch_tc_gemm_nt<128>(e, tmA, tmB, a, epi, st);
 }
 
 static int prepare_tc(xotb200_engine* e) {
@@ -369,7 +375,7 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
       CK(cudaGetLastError());
       TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F};
       if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 2], u, TCE_STORE, st)) return rc;
-      tc_swiglu_kernel<<<S, 256, 0, st>>>(e->tc_gu, e->tc_act, F);
+      tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F);
       CK(cudaGetLastError());
       TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D};
       if (int rc = launch_tc_gemm(e, e->tm_act, e->tm_w[4 * li + 3], d, TCE_RESID, st)) return rc;

@@ -363,14 +363,23 @@ __global__ void __launch_bounds__(128) tc_attn_prefill_kernel(const bf16* q_all,
 }
 
 // gu [S, 2F] (gate_m, up_m interleaved) -> act [S, F] = bf16( bf16(silu(g)) * u )   (llm_utils.py:491-500)
-__global__ void tc_swiglu_kernel(const bf16* gu, bf16* act, int F) {
+// grid (S, ceil(F/2048)), block 256: each thread turns two 16-byte loads (8 pairs) into one 16-byte store
+__global__ void __launch_bounds__(256) tc_swiglu_kernel(const bf16* gu, bf16* act, int F) {
   const int s = blockIdx.x;
-  const __nv_bfloat162* in = reinterpret_cast<const __nv_bfloat162*>(gu + (size_t)s * 2 * F);
-  for (int m = threadIdx.x; m < F; m += blockDim.x) {
-    const __nv_bfloat162 v = in[m];
-    const float g = __low2float(v), u = __high2float(v);
-    act[(size_t)s * F + m] = f2bf(round_bf(g / (1.0f + expf(-g))) * u);
+  const int m0 = (blockIdx.y * 256 + threadIdx.x) * 8;
+  if (m0 >= F) return;
+  const uint4* in = reinterpret_cast<const uint4*>(gu + (size_t)s * 2 * F + 2 * (size_t)m0);
+  const uint4 a0 = in[0], a1 = in[1];
+  const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float g0 = bf_lo(w[2 * j]), u0 = bf_hi(w[2 * j]);
+    const float g1 = bf_lo(w[2 * j + 1]), u1 = bf_hi(w[2 * j + 1]);
+    __nv_bfloat162 p = __floats2bfloat162_rn(round_bf(g0 / (1.0f + expf(-g0))) * u0, round_bf(g1 / (1.0f + expf(-g1))) * u1);
+    o[j] = *reinterpret_cast<uint32_t*>(&p);
   }
+  *reinterpret_cast<uint4*>(act + (size_t)s * F + m0) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // lowest-index arg-max of logits[0..V) -> ctl->token   (single block of 1024 threads)
