@@ -525,17 +525,38 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
         else { xin = a.x; nw = a.final_norm; }
         const uint4* xin4 = reinterpret_cast<const uint4*>(xin);
         if (nw) {
-          // RMSNorm, torchtune<=0.6 / HF order (App. A.1): fp32 normalise -> bf16 -> * scale (bf16) -> bf16
-          float ss = 0.f;
+          // RMSNorm, torchtune<=0.6 / HF order (App. A.1): fp32 normalise -> bf16 -> * scale (bf16) -> bf16.
+          // x and the norm weights are fetched together into registers (ONE L2 round trip on the critical path: the ring
+          // is full and HBM idles while the consumers sit in this prologue), normalised from registers, stored once.
+          constexpr int PC = 4;                                   // chunks of 8 per thread held in registers: K <= 8192
           const bool seed_x = (o.kind == OP_QKV && o.li == 0 && blockIdx.x == 0);   // CTA 0 materialises the residual stream
-          for (int c = threadIdx.x; c < K / 8; c += CONS_THREADS) {
+          const int nch = K / 8;
+          uint4 xv[PC], gv[PC];
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < PC; ++j) {
+            const int c = threadIdx.x + j * CONS_THREADS;
+            if (c < nch) { xv[j] = __ldcg(xin4 + c); gv[j] = __ldg(reinterpret_cast<const uint4*>(nw) + c); }
+          }
+#pragma unroll
+          for (int j = 0; j < PC; ++j) {
+            const int c = threadIdx.x + j * CONS_THREADS;
+            if (c < nch) {
+              if (seed_x) reinterpret_cast<uint4*>(a.x)[c] = xv[j];
+              float f[8];
+              unpack8(xv[j], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+            }
+          }
+          for (int c = threadIdx.x + PC * CONS_THREADS; c < nch; c += CONS_THREADS) {   // K > 8192: spill through x_s
             const uint4 v = __ldcg(xin4 + c);
             reinterpret_cast<uint4*>(x_s)[c] = v;
             if (seed_x) reinterpret_cast<uint4*>(a.x)[c] = v;
             float f[8];
             unpack8(v, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+            for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
           }
           ss = warp_sum(ss);
           if (lane == 0) red[warp] = ss;
@@ -544,22 +565,27 @@ __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArg
 #pragma unroll
           for (int w = 0; w < NCW; ++w) tot += red[w];
           const float rstd = 1.0f / sqrtf(tot / (float)K + a.eps);
-          for (int c = threadIdx.x; c < K / 8; c += CONS_THREADS) {
-            const uint4 v = reinterpret_cast<uint4*>(x_s)[c];
-            const uint4 g = __ldg(reinterpret_cast<const uint4*>(nw) + c);
+          auto norm_store = [&](int c, const uint4& v, const uint4& g) {
             float f[8], sc[8];
             unpack8(v, f);
             unpack8(g, sc);
             uint32_t ov[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float y0 = round_bf(f[2 * j] * rstd) * sc[2 * j];
-              const float y1 = round_bf(f[2 * j + 1] * rstd) * sc[2 * j + 1];
+            for (int i = 0; i < 4; ++i) {
+              const float y0 = round_bf(f[2 * i] * rstd) * sc[2 * i];
+              const float y1 = round_bf(f[2 * i + 1] * rstd) * sc[2 * i + 1];
               __nv_bfloat162 p2 = __floats2bfloat162_rn(y0, y1);
-              ov[j] = *reinterpret_cast<uint32_t*>(&p2);
+              ov[i] = *reinterpret_cast<uint32_t*>(&p2);
             }
             reinterpret_cast<uint4*>(x_s)[c] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+          };
+#pragma unroll
+          for (int j = 0; j < PC; ++j) {
+            const int c = threadIdx.x + j * CONS_THREADS;
+            if (c < nch) norm_store(c, xv[j], gv[j]);
           }
+          for (int c = threadIdx.x + PC * CONS_THREADS; c < nch; c += CONS_THREADS)
+            norm_store(c, reinterpret_cast<uint4*>(x_s)[c], __ldg(reinterpret_cast<const uint4*>(nw) + c));
         } else {
           for (int c = threadIdx.x; c < K / 8; c += CONS_THREADS) reinterpret_cast<uint4*>(x_s)[c] = __ldcg(xin4 + c);
         }
