@@ -174,10 +174,12 @@ def test_ring_mode_equals_api_mode(split):
 # ------------------------------------------------------------------------------------------------------------------
 def _cut(shape_name, n_layers):
   import dataclasses
-  return dataclasses.replace(PRESETS[shape_name], n_layers=n_layers, name=f"{shape_name}-cut{n_layers}")
+  # the 70B card is fp16 upstream; the engine is bf16-only so far: same dimensions, bf16 weights
+  return dataclasses.replace(PRESETS[shape_name], n_layers=n_layers, name=f"{shape_name}-cut{n_layers}", dtype="bfloat16")
 
 
-@pytest.mark.parametrize("shape_name,n_layers,n_prompt,n_gen", [("llama-3-8b", 2, 12, 6), ("llama-3.2-1b", 3, 12, 6)])
+@pytest.mark.parametrize("shape_name,n_layers,n_prompt,n_gen", [("llama-3-8b", 2, 12, 6), ("llama-3.2-1b", 3, 12, 6),
+                                                                 ("llama-3-70b", 2, 12, 4)])
 def test_real_dims_match_oracle_teacher_forced(shape_name, n_layers, n_prompt, n_gen):
   from oracle.ref_engine import RefEngine, RefShard, model_config_from_hf, generate_ids
   from oracle.synth_fast import synth_state_dict_fast

@@ -117,7 +117,7 @@ struct xotb200_engine {
   unsigned int* bar_counter = nullptr;
   void* mega = nullptr;
   size_t mega_smem = 0;
-  int mega_xbuf = 0, mega_grid = 0;
+  int mega_xbuf = 0, mega_grid = 0, mega_nstage = 0;
   int cta_limit = 0;
   // tensor-core prefill (prefill_tc.cuh)
   int prefill_mode = 0;            // 0 auto (TC when n_tokens >= 8), 1 always the decode kernel, 2 always TC
@@ -134,25 +134,39 @@ struct xotb200_engine {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Every copy / memset is ordered on the ENGINE stream (created cudaStreamNonBlocking: the legacy default stream does
+// not synchronise with it, so plain cudaMemcpy/cudaMemset would race with the engine's kernels).
+#define MEMSET_SYNC(e, ptr, val, bytes)                         \
+  do {                                                          \
+    CK(cudaMemsetAsync((ptr), (val), (bytes), (e)->stream));    \
+    CK(cudaStreamSynchronize((e)->stream));                     \
+  } while (0)
+#define MEMCPY_SYNC(e, dst, src, bytes, kind)                        \
+  do {                                                               \
+    CK(cudaMemcpyAsync((dst), (src), (bytes), (kind), (e)->stream)); \
+    CK(cudaStreamSynchronize((e)->stream));                          \
+  } while (0)
+
 // --------------------------------------------------------------------------------------------------------------
 // megakernel dispatch
 // --------------------------------------------------------------------------------------------------------------
 typedef void (*mega_fn)(const MegaArgs);
 
-template <int TK, int HD>
+template <int TK, int HD, int NS>
 static mega_fn pick_mega_r(int R) {
   switch (R) {
-    case 2: return shard_step_kernel<TK, HD, 2>;
-    case 4: return shard_step_kernel<TK, HD, 4>;
-    case 8: return shard_step_kernel<TK, HD, 8>;
+    case 2: return shard_step_kernel<TK, HD, 2, NS>;
+    case 4: return shard_step_kernel<TK, HD, 4, NS>;
+    case 8: return shard_step_kernel<TK, HD, 8, NS>;
     default: return nullptr;
   }
 }
-static mega_fn pick_mega(int tk, int hd, int R) {
-  if (tk == 2048 && hd == 128) return pick_mega_r<2048, 128>(R);
-  if (tk == 2048 && hd == 64) return pick_mega_r<2048, 64>(R);
-  if (tk == 512 && hd == 128) return pick_mega_r<512, 128>(R);
-  if (tk == 512 && hd == 64) return pick_mega_r<512, 64>(R);
+static mega_fn pick_mega(int tk, int hd, int R, int ns) {
+  if (tk == 2048 && hd == 128 && ns == 12) return pick_mega_r<2048, 128, 12>(R);
+  if (tk == 2048 && hd == 64 && ns == 12) return pick_mega_r<2048, 64, 12>(R);
+  if (tk == 2048 && hd == 128 && ns == 8) return pick_mega_r<2048, 128, 8>(R);    // very wide models (70B: 56 KiB activation buffer)
+  if (tk == 512 && hd == 128 && ns == 12) return pick_mega_r<512, 128, 12>(R);
+  if (tk == 512 && hd == 64 && ns == 12) return pick_mega_r<512, 64, 12>(R);
   return nullptr;
 }
 
@@ -166,14 +180,18 @@ static int prepare_mega(xotb200_engine* e) {
   const int tk = e->tk;
   REQUIRE(tk == 2048 || tk == 512, "no shard set");
   const int R = c.n_heads / c.n_kv_heads;
-  mega_fn fn = pick_mega(tk, c.head_dim, R);
-  REQUIRE(fn != nullptr, "no megakernel instantiation for tk=%d head_dim=%d gqa=%d", tk, c.head_dim, R);
   const size_t kmax = (size_t)std::max(std::max(c.dim, c.ffn), qdim);
   const size_t attn_scratch = ((size_t)NCW * R * 2 + (size_t)NCW * R * c.head_dim) * 4;
   const size_t xbuf = align_up(std::max(kmax * 2, attn_scratch), 128);
-  const size_t smem = (size_t)mk_nstage(tk) * mk_stage_bytes(tk) + xbuf + (size_t)(2 * mk_nstage(tk) + 2 * MK_NSLOT) * 8 +
-                      (size_t)MK_NSLOT * NCW * 8 * 4 + 128 + 128 + (size_t)c.n_layers * sizeof(LayerDev);
-  REQUIRE(smem <= SMEM_BUDGET, "shared memory %zu > %zu: activation width %zu too large for the ring", smem, SMEM_BUDGET, kmax);
+  const size_t fixed = xbuf + (size_t)(2 * mk_nstage(tk) + 2 * MK_NSLOT) * 8 + (size_t)MK_NSLOT * NCW * 8 * 4 + 128 + 128 +
+                       (size_t)c.n_layers * sizeof(LayerDev) + 2048 /* static __shared__ */;
+  REQUIRE(fixed + 4 * (size_t)mk_stage_bytes(tk) <= SMEM_BUDGET, "activation width %zu too large for a 4-stage ring", kmax);
+  const int nstage = (SMEM_BUDGET - fixed) / mk_stage_bytes(tk) >= 12 ? 12 : 8;
+  REQUIRE(fixed + (size_t)nstage * mk_stage_bytes(tk) <= SMEM_BUDGET, "activation width %zu too large for an 8-stage ring", kmax);
+  mega_fn fn = pick_mega(tk, c.head_dim, R, nstage);
+  REQUIRE(fn != nullptr, "no megakernel instantiation for tk=%d head_dim=%d gqa=%d stages=%d", tk, c.head_dim, R, nstage);
+  const size_t smem = (size_t)nstage * mk_stage_bytes(tk) + fixed - 2048;
+  e->mega_nstage = nstage;
   CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, MK_THREADS, smem));
@@ -303,9 +321,9 @@ static int prepare_tc(xotb200_engine* e) {
     CK(cudaMalloc(&e->tc_ao, TC_M * qd * 2));
     CK(cudaMalloc(&e->tc_gu, TC_M * 2 * F * 2));
     CK(cudaMalloc(&e->tc_act, TC_M * F * 2));
-    CK(cudaMemset(e->tc_xn, 0, TC_M * D * 2));
-    CK(cudaMemset(e->tc_ao, 0, TC_M * qd * 2));
-    CK(cudaMemset(e->tc_act, 0, TC_M * F * 2));
+    MEMSET_SYNC(e, e->tc_xn, 0, TC_M * D * 2);
+    MEMSET_SYNC(e, e->tc_ao, 0, TC_M * qd * 2);
+    MEMSET_SYNC(e, e->tc_act, 0, TC_M * F * 2);
     if (int rc = make_tmap_act(&e->tm_xn, e->tc_xn, (int)D)) return rc;
     if (int rc = make_tmap_act(&e->tm_ao, e->tc_ao, (int)qd)) return rc;
     if (int rc = make_tmap_act(&e->tm_act, e->tc_act, (int)F)) return rc;
@@ -554,20 +572,20 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   CK(cudaMalloc(&e->part_ml, (size_t)Hq * e->nsplit * 2 * 4));
   CK(cudaMalloc(&e->part_acc, (size_t)Hq * e->nsplit * hd * 4));
   CK(cudaMalloc(&e->tickets, (Hkv + 1) * 4));
-  CK(cudaMemset(e->tickets, 0, (Hkv + 1) * 4));
+  MEMSET_SYNC(e, e->tickets, 0, (Hkv + 1) * 4);
   CK(cudaMalloc(&e->cta_best_val, 1024 * 4));
   CK(cudaMalloc(&e->cta_best_idx, 1024 * 4));
   CK(cudaMalloc(&e->bar_counter, 4));
   CK(cudaMalloc(&e->ctl, sizeof(StepCtl)));
-  CK(cudaMemset(e->ctl, 0, sizeof(StepCtl)));
+  MEMSET_SYNC(e, e->ctl, 0, sizeof(StepCtl));
   const size_t inbox_bytes = sizeof(InboxHdr) + (size_t)2 * D * 2;
   CK(cudaMalloc(&e->inbox, inbox_bytes));
-  CK(cudaMemset(e->inbox, 0, inbox_bytes));
+  MEMSET_SYNC(e, e->inbox, 0, inbox_bytes);
   CK(cudaMalloc(&e->tokens_log, MAX_RING_STEPS * 4));
   CK(cudaMalloc(&e->t_in, MAX_RING_STEPS * 8));
   CK(cudaMalloc(&e->t_out, MAX_RING_STEPS * 8));
-  CK(cudaMemset(e->t_in, 0, MAX_RING_STEPS * 8));
-  CK(cudaMemset(e->t_out, 0, MAX_RING_STEPS * 8));
+  MEMSET_SYNC(e, e->t_in, 0, MAX_RING_STEPS * 8);
+  MEMSET_SYNC(e, e->t_out, 0, MAX_RING_STEPS * 8);
   *out = e;
   return 0;
 }
@@ -791,7 +809,7 @@ int xotb200_begin_request(xotb200_engine* e, int max_total_len) {
       }
     if (e->rope) { CK(cudaFree(e->rope)); e->rope = nullptr; }
     CK(cudaMalloc(&e->rope, tab.size() * sizeof(float2)));
-    CK(cudaMemcpy(e->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    MEMCPY_SYNC(e, e->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
     e->rope_len = max_total_len;
   }
   {  // device-side layer table (weights + this request's KV pointers)
@@ -803,7 +821,7 @@ int xotb200_begin_request(xotb200_engine* e, int max_total_len) {
                        e->kv + (li * 2 + 1) * (size_t)c.n_kv_heads * e->L * c.head_dim};
     }
     if (!e->d_layers) CK(cudaMalloc(&e->d_layers, nl * sizeof(LayerDev)));
-    CK(cudaMemcpy(e->d_layers, h.data(), nl * sizeof(LayerDev), cudaMemcpyHostToDevice));
+    MEMCPY_SYNC(e, e->d_layers, h.data(), nl * sizeof(LayerDev), cudaMemcpyHostToDevice);
   }
   // reset_caches (llm_utils.py:409-414): zero like torchtune's KVCache.reset
   CK(cudaMemsetAsync(e->kv, 0, nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim * 2, e->stream));
@@ -877,7 +895,7 @@ int xotb200_last_token(xotb200_engine* e, int32_t* token) {
   REQUIRE(e->last && e->have_result, "no last-shard result available");
   CK(cudaSetDevice(e->device));
   StepCtl h;
-  CK(cudaMemcpy(&h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+  MEMCPY_SYNC(e, &h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost);
   *token = h.token;
   return 0;
 }
@@ -960,16 +978,16 @@ int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   StepCtl h;
-  CK(cudaMemcpy(&h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+  MEMCPY_SYNC(e, &h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost);
   if (h.err) {
-    CK(cudaMemset(&e->ctl->err, 0, 4));
+    MEMSET_SYNC(e, &e->ctl->err, 0, 4);
     set_err("ring step %d: timed out waiting for the previous shard's flag", h.step);
     return XOTB200_ETIMEOUT;
   }
   if (tokens_out) {
     REQUIRE(e->last, "tokens are produced on the last shard");
     REQUIRE(n_steps <= e->last_ring_steps, "n_steps exceeds the last ring run");
-    CK(cudaMemcpy(tokens_out, e->tokens_log, (size_t)n_steps * 4, cudaMemcpyDeviceToHost));
+    MEMCPY_SYNC(e, tokens_out, e->tokens_log, (size_t)n_steps * 4, cudaMemcpyDeviceToHost);
   }
   if (ms_out) CK(cudaEventElapsedTime(ms_out, e->ev0, e->ev1));
   e->have_result = true;
@@ -979,8 +997,8 @@ int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float
 int xotb200_ring_timestamps(xotb200_engine* e, uint64_t* t_in, uint64_t* t_out, int n_steps) {
   REQUIRE(e && t_in && t_out && n_steps <= MAX_RING_STEPS, "bad argument");
   CK(cudaSetDevice(e->device));
-  CK(cudaMemcpy(t_in, e->t_in, (size_t)n_steps * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(t_out, e->t_out, (size_t)n_steps * 8, cudaMemcpyDeviceToHost));
+  MEMCPY_SYNC(e, t_in, e->t_in, (size_t)n_steps * 8, cudaMemcpyDeviceToHost);
+  MEMCPY_SYNC(e, t_out, e->t_out, (size_t)n_steps * 8, cudaMemcpyDeviceToHost);
   return 0;
 }
 
@@ -1007,9 +1025,9 @@ int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16
   CK(cudaMalloc(&dW0, (size_t)N * K * 2));
   CK(cudaMalloc(&dW, (size_t)N * K * 2));
   CK(cudaMalloc(&dO, (size_t)TC_M * N * 2));
-  CK(cudaMemset(dA, 0, (size_t)TC_M * K * 2));
-  CK(cudaMemcpy(dA, a_bf16, (size_t)S * K * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dW0, w_bf16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+  MEMSET_SYNC(e, dA, 0, (size_t)TC_M * K * 2);
+  MEMCPY_SYNC(e, dA, a_bf16, (size_t)S * K * 2, cudaMemcpyHostToDevice);
+  MEMCPY_SYNC(e, dW0, w_bf16, (size_t)N * K * 2, cudaMemcpyHostToDevice);
   relayout_rows_kernel<<<N, 128, 0, e->stream>>>(dW0, dW, N, K, 0, e->cfg.head_dim, 1, 0, N, tk);
   CK(cudaGetLastError());
   CUtensorMap tA, tB;
@@ -1020,7 +1038,10 @@ int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16
     rc = launch_tc_gemm(e, tA, tB, g, TCE_STORE, e->stream);
   }
   cudaError_t er = cudaStreamSynchronize(e->stream);
-  if (!rc && er == cudaSuccess) er = cudaMemcpy(out_bf16, dO, (size_t)S * N * 2, cudaMemcpyDeviceToHost);
+  if (!rc && er == cudaSuccess) {
+    er = cudaMemcpyAsync(out_bf16, dO, (size_t)S * N * 2, cudaMemcpyDeviceToHost, e->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(e->stream);
+  }
   cudaFree(dA); cudaFree(dW0); cudaFree(dW); cudaFree(dO);
   if (rc) return rc;
   CK(er);
@@ -1031,11 +1052,11 @@ int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, 
   REQUIRE(e, "null engine");
   CK(cudaSetDevice(e->device));
   const size_t cap = (size_t)(4 * e->cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8;
-  if (!e->dbg) { CK(cudaMalloc(&e->dbg, cap * 8)); CK(cudaMemset(e->dbg, 0, cap * 8)); }
+  if (!e->dbg) { CK(cudaMalloc(&e->dbg, cap * 8)); MEMSET_SYNC(e, e->dbg, 0, cap * 8); }
   if (out) {
     REQUIRE(n_u64 >= 0 && (size_t)n_u64 <= cap, "n_u64 too large (max %zu)", cap);
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(out, e->dbg, (size_t)n_u64 * 8, cudaMemcpyDeviceToHost));
+    MEMCPY_SYNC(e, out, e->dbg, (size_t)n_u64 * 8, cudaMemcpyDeviceToHost);
   }
   e->dbg_step = step;
   e->dbg_cta = cta;

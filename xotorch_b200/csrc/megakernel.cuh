@@ -33,7 +33,7 @@ constexpr int MK_NSLOT = 4;               // partial-sum hand-off slots consumer
 // 1.4 % faster than 32 KiB x 6) or 8 KiB x 12 (tiny parity shapes)
 __host__ __device__ constexpr int mk_rows(int tk) { return tk >= 2048 ? 4 : 8; }
 __host__ __device__ constexpr int mk_stage_bytes(int tk) { return mk_rows(tk) * tk * 2; }
-__host__ __device__ constexpr int mk_nstage(int tk) { return 12; }
+__host__ __device__ constexpr int mk_nstage(int tk) { return 12; }   // default ring depth (8 for very wide models, see engine.cu)
 
 
 __device__ __forceinline__ void bar_sync(int id, int count) {
@@ -365,13 +365,12 @@ __device__ __forceinline__ void attn_phase(const MegaArgs& a, const LayerDev& lw
 // transpose-reduce per row group.  Partials go to the epilogue warp through a 4-slot mbarrier mailbox; it adds them
 // in fixed order (deterministic) and applies the fused epilogue.
 // ------------------------------------------------------------------------------------------------------------
-template <int TK, int HD, int R>
+template <int TK, int HD, int R, int NSTAGE>
 __global__ void __launch_bounds__(MK_THREADS, 1) shard_step_kernel(const MegaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int MK_ROWS = mk_rows(TK);            // weight rows per ring stage
   constexpr int ROWB = TK * 2;                    // bytes per stage row
   constexpr int STAGE_BYTES = mk_stage_bytes(TK);
-  constexpr int NSTAGE = mk_nstage(TK);
   constexpr int CB = TK / 256;                    // column blocks per stage (a lane covers 8 columns, a warp 256)
   constexpr int RS = NCW / CB;                    // row subsets per stage
   constexpr int RPW = MK_ROWS / RS;               // rows per consumer warp per stage
