@@ -101,6 +101,8 @@ PRESETS: Dict[str, ModelShape] = {
                              rope_scaling=dict(_LLAMA32_SCALING)),
   "llama-3-8b": ModelShape("llama-3-8b", 32, 4096, 14336, 32, 8, 128, 128256),
   "llama-3-70b": ModelShape("llama-3-70b", 80, 8192, 28672, 64, 8, 128, 128256, dtype="float16"),
+  # same dimensions with bf16 weights: what the engine runs today (fp16 weights are not implemented yet)
+  "llama-3-70b-bf16": ModelShape("llama-3-70b-bf16", 80, 8192, 28672, 64, 8, 128, 128256),
 }
 
 
