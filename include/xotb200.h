@@ -31,7 +31,7 @@ extern "C" {
 #define XOTB200_ETIMEOUT (-5) /* device-side wait on a peer flag expired  */
 
 #define XOTB200_DTYPE_BF16 0
-#define XOTB200_DTYPE_F16 1 /* reserved: 70B fp16 config */
+#define XOTB200_DTYPE_F16 1 /* IEEE half weights / activations / KV (the 70B card upstream is fp16); fp32 accumulation as for bf16 */
 
 #define XOTB200_ROPE_PLAIN 0  /* RotaryPositionalEmbeddings (general_mha.py:57-63, and llama ids w/o rope_scaling: App. B3) */
 #define XOTB200_ROPE_LLAMA3 1 /* Llama3ScaledRoPE (general_mha.py:33-40)                                              */
@@ -76,7 +76,7 @@ int xotb200_destroy(xotb200_engine* e);
 int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer);
 /* set_shard + read every *.safetensors in `dir` (HF names, HF layout; q/k re-laid out like _permute, llm_utils.py:175-183) */
 int xotb200_load_shard(xotb200_engine* e, const char* safetensors_dir, int start_layer, int end_layer);
-/* one tensor by HF name from a host buffer (bf16 bits); tensors outside the shard are ignored (returns 1) */
+/* one tensor by HF name from a host buffer (16-bit patterns in the engine's dtype); tensors outside the shard are ignored (returns 1) */
 int xotb200_load_tensor(xotb200_engine* e, const char* hf_name, const void* host_data, const int64_t* shape, int ndim);
 /* fill the current shard with the counter-based synthetic weights of xotorch_b200/synth.py, generated on device */
 int xotb200_init_synthetic(xotb200_engine* e, uint64_t seed);

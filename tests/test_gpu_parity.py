@@ -62,7 +62,8 @@ def _api_generate(engines, prompt, n_gen, force_ids=None, max_len=None):
   return np.array(ids, dtype=np.int32), np.stack(logits_all)
 
 
-@pytest.mark.parametrize("shape_name", ["tiny-llama-hd64", "tiny-llama-hd128", "tiny-llama-3.2"])
+@pytest.mark.parametrize("shape_name", ["tiny-llama-hd64", "tiny-llama-hd128", "tiny-llama-3.2", "tiny-llama-hd64-f16",
+                                        "tiny-llama-hd128-f16"])
 def test_logits_match_oracle_teacher_forced(shape_name):
   shape = PRESETS[shape_name]
   full = [(0, shape.n_layers - 1)]
@@ -92,7 +93,7 @@ def test_greedy_ids_match_oracle():
 
 
 @pytest.mark.parametrize("shape_name,split", [("tiny-llama-hd64", [(0, 1), (2, 3)]), ("tiny-llama-hd64", [(0, 0), (1, 2), (3, 3)]),
-                                              ("tiny-llama-3.2", [(0, 2), (3, 3)])])
+                                              ("tiny-llama-3.2", [(0, 2), (3, 3)]), ("tiny-llama-hd64-f16", [(0, 1), (2, 3)])])
 def test_sharded_equals_unsharded_bit_exact(shape_name, split):
   shape = PRESETS[shape_name]
   prompt = synth_prompt(shape.vocab, 12)
@@ -102,8 +103,8 @@ def test_sharded_equals_unsharded_bit_exact(shape_name, split):
   assert np.array_equal(logits_f, logits_s)
 
 
-def test_safetensors_loader_equals_device_synth(tmp_path):
-  shape_name = "tiny-llama-hd64"
+@pytest.mark.parametrize("shape_name", ["tiny-llama-hd64", "tiny-llama-hd64-f16"])
+def test_safetensors_loader_equals_device_synth(tmp_path, shape_name):
   shape = PRESETS[shape_name]
   d = write_hf_dir(tmp_path / "m", shape, 1234)
   prompt = synth_prompt(shape.vocab, 9)
@@ -122,10 +123,10 @@ def test_strict_loader_reports_missing(tmp_path):
     e.check_loaded()
 
 
-@pytest.mark.parametrize("split", [[(0, 3)], [(0, 1), (2, 3)], [(0, 0), (1, 2), (3, 3)]])
-def test_ring_mode_equals_api_mode(split):
-  """Device-resident ring (CUDA-graph steps, inbox flags, on-device argmax feedback) == step-by-step host API."""
-  shape_name = "tiny-llama-hd64"
+@pytest.mark.parametrize("split,shape_name", [([(0, 3)], "tiny-llama-hd64"), ([(0, 1), (2, 3)], "tiny-llama-hd64"),
+                                              ([(0, 0), (1, 2), (3, 3)], "tiny-llama-hd64"), ([(0, 1), (2, 3)], "tiny-llama-hd64-f16")])
+def test_ring_mode_equals_api_mode(split, shape_name):
+  """Device-resident ring (persistent kernel, inbox flags, on-device argmax feedback) == step-by-step host API."""
   shape = PRESETS[shape_name]
   prompt = synth_prompt(shape.vocab, 10)
   n_gen = 20

@@ -37,7 +37,8 @@ def test_tcgen05_gemm_matches_numpy(S, N, K, tk):
   assert np.mean(out == ref_bf) > 0.97
 
 
-@pytest.mark.parametrize("shape_name,n_prompt", [("tiny-llama-hd64", 40), ("tiny-llama-hd128", 131), ("tiny-llama-3.2", 200)])
+@pytest.mark.parametrize("shape_name,n_prompt", [("tiny-llama-hd64", 40), ("tiny-llama-hd128", 131), ("tiny-llama-3.2", 200),
+                                                 ("tiny-llama-hd128-f16", 140)])
 def test_tc_prefill_matches_oracle_and_decode_kernel_path(shape_name, n_prompt):
   shape = PRESETS[shape_name]
   full = [(0, shape.n_layers - 1)]

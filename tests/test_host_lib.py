@@ -54,8 +54,9 @@ def test_cfg_from_hf_follows_reference_mapping():
   assert c.rope_kind == _lib.ROPE_PLAIN and c.tie_embeddings == 0          # App. B3: no rope_scaling -> unscaled
   c = cfg_from_hf(hf_config(PRESETS["llama-3.2-1b"]))
   assert c.rope_kind == _lib.ROPE_LLAMA3 and c.rope_factor == 32.0 and c.tie_embeddings == 1
+  assert cfg_from_hf(hf_config(PRESETS["llama-3-70b"])).dtype == _lib.DTYPE_F16          # the upstream 70B card is fp16
   with pytest.raises(ValueError):
-    cfg_from_hf({**hf_config(PRESETS["llama-3-8b"]), "torch_dtype": "float16"})
+    cfg_from_hf({**hf_config(PRESETS["llama-3-8b"]), "torch_dtype": "float32"})
 
 
 def test_synth_generators_agree():

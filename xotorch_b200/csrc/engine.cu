@@ -34,6 +34,30 @@
 #include "megakernel.cuh"
 #include "prefill_tc.cuh"
 
+// The dtype-dependent helpers and kernels are compiled twice: xb::bf (bfloat16 weights) and xb::fp (IEEE half weights).
+namespace xb {
+namespace bf {
+#define XB_DT 0
+#include "dtype_impl.inc"
+#include "megakernel_impl.inc"
+#include "prefill_tc_impl.inc"
+#undef XB_DT
+}  // namespace bf
+namespace fp {
+#define XB_DT 1
+#include "dtype_impl.inc"
+#include "megakernel_impl.inc"
+#include "prefill_tc_impl.inc"
+#undef XB_DT
+}  // namespace fp
+}  // namespace xb
+// launch the bf16 or the fp16 instantiation of a kernel expression
+#define DT_LAUNCH(e, call)                 \
+  do {                                     \
+    if ((e)->cfg.dtype == XOTB200_DTYPE_F16) { using namespace xb::fp; call; } \
+    else { using namespace xb::bf; call; } \
+  } while (0)
+
 using namespace xb;
 
 // --------------------------------------------------------------------------------------------------------------
@@ -152,22 +176,28 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // --------------------------------------------------------------------------------------------------------------
 typedef void (*mega_fn)(const MegaArgs);
 
-template <int TK, int HD, int NS>
-static mega_fn pick_mega_r(int R) {
-  switch (R) {
-    case 2: return shard_step_kernel<TK, HD, 2, NS>;
-    case 4: return shard_step_kernel<TK, HD, 4, NS>;
-    case 8: return shard_step_kernel<TK, HD, 8, NS>;
-    default: return nullptr;
+#define PICK_MEGA_NS(NSP)                                                                                   \
+  template <int TK, int HD, int NS>                                                                          \
+  static mega_fn pick_mega_r_##NSP(int R) {                                                                  \
+    switch (R) {                                                                                             \
+      case 2: return xb::NSP::shard_step_kernel<TK, HD, 2, NS>;                                              \
+      case 4: return xb::NSP::shard_step_kernel<TK, HD, 4, NS>;                                              \
+      case 8: return xb::NSP::shard_step_kernel<TK, HD, 8, NS>;                                              \
+      default: return nullptr;                                                                               \
+    }                                                                                                        \
+  }                                                                                                          \
+  static mega_fn pick_mega_##NSP(int tk, int hd, int R, int ns) {                                            \
+    if (tk == 2048 && hd == 128 && ns == 12) return pick_mega_r_##NSP<2048, 128, 12>(R);                    \
+    if (tk == 2048 && hd == 64 && ns == 12) return pick_mega_r_##NSP<2048, 64, 12>(R);                      \
+    if (tk == 2048 && hd == 128 && ns == 8) return pick_mega_r_##NSP<2048, 128, 8>(R); /* very wide (70B) */ \
+    if (tk == 512 && hd == 128 && ns == 12) return pick_mega_r_##NSP<512, 128, 12>(R);                      \
+    if (tk == 512 && hd == 64 && ns == 12) return pick_mega_r_##NSP<512, 64, 12>(R);                        \
+    return nullptr;                                                                                          \
   }
-}
-static mega_fn pick_mega(int tk, int hd, int R, int ns) {
-  if (tk == 2048 && hd == 128 && ns == 12) return pick_mega_r<2048, 128, 12>(R);
-  if (tk == 2048 && hd == 64 && ns == 12) return pick_mega_r<2048, 64, 12>(R);
-  if (tk == 2048 && hd == 128 && ns == 8) return pick_mega_r<2048, 128, 8>(R);    // very wide models (70B: 56 KiB activation buffer)
-  if (tk == 512 && hd == 128 && ns == 12) return pick_mega_r<512, 128, 12>(R);
-  if (tk == 512 && hd == 64 && ns == 12) return pick_mega_r<512, 64, 12>(R);
-  return nullptr;
+PICK_MEGA_NS(bf)
+PICK_MEGA_NS(fp)
+static mega_fn pick_mega(int tk, int hd, int R, int ns, int dtype) {
+  return dtype == XOTB200_DTYPE_F16 ? pick_mega_fp(tk, hd, R, ns) : pick_mega_bf(tk, hd, R, ns);
 }
 
 static const size_t SMEM_BUDGET = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
@@ -188,7 +218,7 @@ static int prepare_mega(xotb200_engine* e) {
   REQUIRE(fixed + 4 * (size_t)mk_stage_bytes(tk) <= SMEM_BUDGET, "activation width %zu too large for a 4-stage ring", kmax);
   const int nstage = (SMEM_BUDGET - fixed) / mk_stage_bytes(tk) >= 12 ? 12 : 8;
   REQUIRE(fixed + (size_t)nstage * mk_stage_bytes(tk) <= SMEM_BUDGET, "activation width %zu too large for an 8-stage ring", kmax);
-  mega_fn fn = pick_mega(tk, c.head_dim, R, nstage);
+  mega_fn fn = pick_mega(tk, c.head_dim, R, nstage, c.dtype);
   REQUIRE(fn != nullptr, "no megakernel instantiation for tk=%d head_dim=%d gqa=%d stages=%d", tk, c.head_dim, R, nstage);
   const size_t smem = (size_t)nstage * mk_stage_bytes(tk) + fixed - 2048;
   e->mega_nstage = nstage;
@@ -284,10 +314,11 @@ template <int NT>
 static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
                              cudaStream_t st) {
   void (*fn)(CUtensorMap, CUtensorMap, TcGemmArgs) = nullptr;
+  const bool f16 = e->cfg.dtype == XOTB200_DTYPE_F16;
   switch (epi) {
-    case TCE_STORE: fn = tc_gemm_kernel<NT, TCE_STORE>; break;
-    case TCE_RESID: fn = tc_gemm_kernel<NT, TCE_RESID>; break;
-    default: fn = tc_gemm_kernel<NT, TCE_HEAD_LAST>; break;
+    case TCE_STORE: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_STORE> : xb::bf::tc_gemm_kernel<NT, TCE_STORE>; break;
+    case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_RESID> : xb::bf::tc_gemm_kernel<NT, TCE_RESID>; break;
+    default: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_HEAD_LAST> : xb::bf::tc_gemm_kernel<NT, TCE_HEAD_LAST>; break;
   }
   static std::map<std::pair<int, void*>, bool> attr_done;
   auto key = std::make_pair(e->device, (void*)fn);
@@ -348,9 +379,9 @@ static int launch_tc_attn(xotb200_engine* e, int S, int R, bf16* kc, bf16* vc, i
   dim3 grid(S, e->cfg.n_kv_heads);
   const float scale = 1.0f / sqrtf((float)HD);
   switch (R) {
-    case 2: tc_attn_prefill_kernel<HD, 2><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale); break;
-    case 4: tc_attn_prefill_kernel<HD, 4><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale); break;
-    case 8: tc_attn_prefill_kernel<HD, 8><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale); break;
+    case 2: DT_LAUNCH(e, (tc_attn_prefill_kernel<HD, 2><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale))); break;
+    case 4: DT_LAUNCH(e, (tc_attn_prefill_kernel<HD, 4><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale))); break;
+    case 8: DT_LAUNCH(e, (tc_attn_prefill_kernel<HD, 8><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale))); break;
     default: set_err("unsupported GQA ratio %d", R); return XOTB200_EINVAL;
   }
   CK(cudaGetLastError());
@@ -378,22 +409,22 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
       const LayerW& w = e->layers[li];
       bf16* kc = e->kv + ((size_t)li * 2 + 0) * Hkv * e->L * hd;
       bf16* vc = e->kv + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
-      tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.attn_norm, e->tc_xn, D, c.norm_eps);
+      DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.attn_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
       TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv};
       if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 0], g, TCE_STORE, st)) return rc;
-      tc_rope_kv_kernel<<<S, 256, 0, st>>>(e->tc_qkv, e->tc_q, kc, vc, e->rope, Hq, Hkv, hd, e->L, pos0 + m0);
+      DT_LAUNCH(e, (tc_rope_kv_kernel<<<S, 256, 0, st>>>(e->tc_qkv, e->tc_q, kc, vc, e->rope, Hq, Hkv, hd, e->L, pos0 + m0)));
       CK(cudaGetLastError());
       if (int rc = (hd == 128 ? launch_tc_attn<128>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)
                               : launch_tc_attn<64>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)))
         return rc;
       TcGemmArgs o{S, D, qd, e->tk, e->tc_x, nullptr, D};
       if (int rc = launch_tc_gemm(e, e->tm_ao, e->tm_w[4 * li + 1], o, TCE_RESID, st)) return rc;
-      tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.mlp_norm, e->tc_xn, D, c.norm_eps);
+      DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.mlp_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
       TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F};
       if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 2], u, TCE_STORE, st)) return rc;
-      tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F);
+      DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F)));
       CK(cudaGetLastError());
       TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D};
       if (int rc = launch_tc_gemm(e, e->tm_act, e->tm_w[4 * li + 3], d, TCE_RESID, st)) return rc;
@@ -401,7 +432,7 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
     }
     if (e->last) {
       if (m0 + S == n_tokens) {   // logits of the last position only (sharded_inference_engine.py:365-368)
-        tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, e->final_norm, e->tc_xn, D, c.norm_eps);
+        DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, e->final_norm, e->tc_xn, D, c.norm_eps)));
         CK(cudaGetLastError());
         TcGemmArgs h{S, c.vocab, D, e->tk, nullptr, e->logits, 0};
         if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * nl], h, TCE_HEAD_LAST, st)) return rc;
@@ -540,7 +571,7 @@ const char* xotb200_version(void) { return "xotb200 0.1.0 sm_100a"; }
 
 int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** out) {
   REQUIRE(cfg && out, "null argument");
-  REQUIRE(cfg->dtype == XOTB200_DTYPE_BF16, "only bf16 weights are implemented (dtype=%d)", cfg->dtype);
+  REQUIRE(cfg->dtype == XOTB200_DTYPE_BF16 || cfg->dtype == XOTB200_DTYPE_F16, "dtype must be bf16 (0) or f16 (1), got %d", cfg->dtype);
   REQUIRE(cfg->head_dim == 64 || cfg->head_dim == 128, "head_dim must be 64 or 128 (got %d)", cfg->head_dim);
   REQUIRE(cfg->n_heads % cfg->n_kv_heads == 0, "n_heads %% n_kv_heads != 0");
   const int R = cfg->n_heads / cfg->n_kv_heads;
@@ -738,7 +769,8 @@ int xotb200_load_shard(xotb200_engine* e, const char* dir, int start_layer, int 
       auto sl = e->slots.find(it->first);
       if (sl == e->slots.end()) continue;
       const StEntry& en = it->second;
-      if (en.dtype != "BF16") { set_err("tensor %s: dtype %s unsupported (BF16 only)", it->first.c_str(), en.dtype.c_str()); rc = XOTB200_EIO; break; }
+      const char* want = e->cfg.dtype == XOTB200_DTYPE_F16 ? "F16" : "BF16";
+      if (en.dtype != want) { set_err("tensor %s: dtype %s but the engine was created for %s", it->first.c_str(), en.dtype.c_str(), want); rc = XOTB200_EIO; break; }
       if ((uint64_t)(8 + hlen + en.end) > (uint64_t)sb.st_size) { set_err("tensor %s: data out of file bounds", it->first.c_str()); rc = XOTB200_EIO; break; }
       rc = xotb200_load_tensor(e, it->first.c_str(), base + 8 + hlen + en.begin, en.shape.data(), (int)en.shape.size());
       if (rc == 1) rc = 0;
@@ -757,7 +789,7 @@ int xotb200_init_synthetic(xotb200_engine* e, uint64_t seed) {
     TensorSlot& s = kv.second;
     const unsigned long long base = seed * 0x9E3779B97F4A7C15ull + (unsigned long long)s.tensor_id * 0xD1B54A32D192ED03ull;
     const float scale = (float)((double)s.std / ih4_std);
-    synth_rows_kernel<<<s.rows, 256, 0, e->stream>>>(s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off, s.n_total, s.panel_tk, base, scale, s.mean);
+    DT_LAUNCH(e, (synth_rows_kernel<<<s.rows, 256, 0, e->stream>>>(s.dst, s.rows, s.K, s.mode, e->cfg.head_dim, s.stride, s.off, s.n_total, s.panel_tk, base, scale, s.mean)));
     CK(cudaGetLastError());
     e->launches++;
     s.loaded = true;
@@ -867,7 +899,7 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
     CK(cudaMemcpyAsync(e->stage_tokens, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st));
   } else {
     CK(cudaMemcpyAsync(e->stage_f32, hidden_f32, (size_t)n_tokens * D * 4, cudaMemcpyHostToDevice, st));
-    f32_to_bf16_kernel<<<256, 256, 0, st>>>(e->stage_f32, e->stage_in, (size_t)n_tokens * D);
+    DT_LAUNCH(e, (f32_to_bf16_kernel<<<256, 256, 0, st>>>(e->stage_f32, e->stage_in, (size_t)n_tokens * D)));
     CK(cudaGetLastError());
     e->launches++;
   }
@@ -880,7 +912,7 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
   if (e->last) {
     CK(cudaMemcpyAsync(out_f32, e->logits, (size_t)e->cfg.vocab * 4, cudaMemcpyDeviceToHost, st));
   } else {
-    bf16_to_f32_kernel<<<256, 256, 0, st>>>(e->stage_out, e->stage_f32, (size_t)n_tokens * D);
+    DT_LAUNCH(e, (bf16_to_f32_kernel<<<256, 256, 0, st>>>(e->stage_out, e->stage_f32, (size_t)n_tokens * D)));
     CK(cudaGetLastError());
     e->launches++;
     CK(cudaMemcpyAsync(out_f32, e->stage_f32, (size_t)n_tokens * D * 4, cudaMemcpyDeviceToHost, st));

@@ -91,23 +91,6 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
-__device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
-__device__ __forceinline__ float round_bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  f[0] = bf_lo(v.x); f[1] = bf_hi(v.x); f[2] = bf_lo(v.y); f[3] = bf_hi(v.y);
-  f[4] = bf_lo(v.z); f[5] = bf_hi(v.z); f[6] = bf_lo(v.w); f[7] = bf_hi(v.w);
-}
-__device__ __forceinline__ float dot8(const uint4& w, const float (&x)[8], float acc) {
-  acc = fmaf(bf_lo(w.x), x[0], acc); acc = fmaf(bf_hi(w.x), x[1], acc);
-  acc = fmaf(bf_lo(w.y), x[2], acc); acc = fmaf(bf_hi(w.y), x[3], acc);
-  acc = fmaf(bf_lo(w.z), x[4], acc); acc = fmaf(bf_hi(w.z), x[5], acc);
-  acc = fmaf(bf_lo(w.w), x[6], acc); acc = fmaf(bf_hi(w.w), x[7], acc);
-  return acc;
-}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -133,14 +116,6 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
 // ------------------------------------------------------------------------------------------------------------
 // small utility kernels
 // ------------------------------------------------------------------------------------------------------------
-__global__ void f32_to_bf16_kernel(const float* in, bf16* out, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = f2bf(in[i]);
-}
-__global__ void bf16_to_f32_kernel(const bf16* in, float* out, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = bf2f(in[i]);
-}
 // post a hidden vector / token into the next inbox and release the flag (used once, after prefill)
 __global__ void post_kernel(InboxHdr* next, const bf16* hidden, int D, const int* token, int step) {
   const int slot = step & 1;
@@ -191,16 +166,4 @@ __device__ __forceinline__ float synth_value(unsigned long long base, unsigned l
   const int s = (int)(z & 0xffff) + (int)((z >> 16) & 0xffff) + (int)((z >> 32) & 0xffff) + (int)(z >> 48);
   return __fadd_rn(__fmul_rn((float)(s - 131070), scale), mean);
 }
-// dst row (see relayout_rows_kernel) takes HF row map(r) of the tensor; same destination layouts.
-__global__ void synth_rows_kernel(bf16* dst, int rows, int K, int mode, int hd, int dst_stride_rows, int dst_row_off,
-                                  int n_total, int panel_tk, unsigned long long base, float scale, float mean) {
-  const int r = blockIdx.x;
-  if (r >= rows) return;
-  const int sr = src_row_of(r, mode, hd);
-  const int rd = dst_row_off + r * dst_stride_rows;
-  for (int c = threadIdx.x; c < K; c += blockDim.x)
-    dst[panel_index(rd, c, K, n_total, panel_tk)] =
-        f2bf(synth_value(base, (unsigned long long)sr * (unsigned long long)K + c, scale, mean));
-}
-
 }  // namespace xb

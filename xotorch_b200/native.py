@@ -18,8 +18,12 @@ def cfg_from_hf(hf: dict) -> ModelCfg:
   (/root/reference/xotorch/inference/llm_utils.py:79-126) with App. B2/B3 fixed (HF rope_scaling keys; unscaled RoPE
   when rope_scaling is null)."""
   dt = str(hf.get("torch_dtype", "bfloat16"))
-  if dt not in ("bfloat16", "bf16"):
-    raise ValueError(f"torch_dtype {dt!r}: libxotb200 implements bf16 weights only")
+  if dt in ("bfloat16", "bf16"):
+    dtype = _lib.DTYPE_BF16
+  elif dt in ("float16", "fp16", "half"):
+    dtype = _lib.DTYPE_F16
+  else:
+    raise ValueError(f"torch_dtype {dt!r}: libxotb200 implements 16-bit weights (bfloat16, float16) with fp32 accumulation")
   rs = hf.get("rope_scaling")
   c = ModelCfg()
   c.n_layers = hf["num_hidden_layers"]
@@ -33,7 +37,7 @@ def cfg_from_hf(hf: dict) -> ModelCfg:
   c.rope_theta = float(hf.get("rope_theta", 10000.0))
   c.norm_eps = float(hf["rms_norm_eps"])
   c.tie_embeddings = 1 if hf.get("tie_word_embeddings", False) else 0
-  c.dtype = _lib.DTYPE_BF16
+  c.dtype = dtype
   if rs is not None:
     c.rope_kind = _lib.ROPE_LLAMA3
     c.rope_factor = float(rs.get("factor", 32))

@@ -95,6 +95,8 @@ PRESETS: Dict[str, ModelShape] = {
   # tiny parity shapes (oracle runs in milliseconds)
   "tiny-llama-hd64": ModelShape("tiny-llama-hd64", 4, 512, 1536, 8, 2, 64, 2048, max_pos=2048),
   "tiny-llama-hd128": ModelShape("tiny-llama-hd128", 3, 1024, 3072, 8, 2, 128, 4096, max_pos=2048),
+  "tiny-llama-hd64-f16": ModelShape("tiny-llama-hd64-f16", 4, 512, 1536, 8, 2, 64, 2048, max_pos=2048, dtype="float16"),
+  "tiny-llama-hd128-f16": ModelShape("tiny-llama-hd128-f16", 3, 1024, 3072, 8, 2, 128, 4096, max_pos=2048, dtype="float16"),
   "tiny-llama-3.2": ModelShape("tiny-llama-3.2", 4, 512, 1536, 8, 2, 64, 2048, max_pos=16384, tie=True,
                                rope_scaling=dict(_LLAMA32_SCALING)),
   "llama-3.2-1b": ModelShape("llama-3.2-1b", 16, 2048, 8192, 32, 8, 64, 128256, max_pos=131072, tie=True,
