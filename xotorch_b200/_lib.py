@@ -72,7 +72,7 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
   global _lib
   if _lib is not None and path is None:
     return _lib
-  p = Path(path) if path else LIB_PATH
+  p = Path(path) if path else Path(os.environ.get("XOTB200_LIB", LIB_PATH))   # XOTB200_LIB: A/B-test another build
   if not p.exists():
     raise ImportError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                       f"or `make -C xotorch_b200/csrc` — xotorch_b200 has no CPU fallback")
