@@ -87,6 +87,13 @@ int xotb200_check_loaded(xotb200_engine* e);
  *      (sharded_inference_engine.py:71-83,133-147) and ShardTransformerDecoder.setup_caches/reset_caches
  *      (llm_utils.py:369-414).  KV capacity comes from the request (App. B7). ---- */
 int xotb200_begin_request(xotb200_engine* e, int max_total_len);
+/* Several independent requests in flight through the ring (each keeps its own KV cache; each is still a batch-1 stream):
+ * ring step s serves request s % n_requests at position pos0 + s / n_requests, so with n_requests >= number of shards
+ * every GPU of the ring is busy all the time (the reference keeps per-request state in Node but its engine
+ * is single-request, sharded_inference_engine.py:250).  1 <= n_requests <= 8.  xotb200_forward / xotb200_post_to_next act on
+ * the request chosen with xotb200_select_request (0 after begin_batch). */
+int xotb200_begin_batch(xotb200_engine* e, int max_total_len, int n_requests);
+int xotb200_select_request(xotb200_engine* e, int request);
 
 /* ---- the step: replaces infer_tensor -> ShardedGeneralModel.generate -> ShardTransformerDecoder.forward
  *      (sharded_inference_engine.py:230-370; general_mha.py:178-254; llm_utils.py:416-489).
@@ -112,7 +119,8 @@ int xotb200_link_next_local(xotb200_engine* e, xotb200_engine* next); /* same pr
 /* Hand the result of the most recent xotb200_forward (hidden state of its last position, or last token) to the
  * next engine's inbox as step `step` — used once after prefill to seed the ring. */
 int xotb200_post_to_next(xotb200_engine* e, int step);
-/* Enqueue n_steps ring steps (CUDA graph replays) starting at ring step `step0`, position `pos0`; asynchronous. */
+/* Launch the persistent kernel for n_steps ring steps starting at ring step `step0`, position `pos0`; asynchronous.
+ * With a batch of B requests n_steps must be a multiple of B (n_steps / B tokens per request) and step0 a multiple of B. */
 int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0);
 /* Wait for the engine's stream; on the last shard copies the n_steps generated token ids (int32) to tokens_out
  * (may be NULL).  ms_out (may be NULL) = device time of the launched steps by CUDA events. */

@@ -262,3 +262,24 @@ def test_error_paths(tmp_path):
   with pytest.raises(XotB200Error, match="shape mismatch"):
     e.load_tensor("model.layers.0.mlp.down_proj.weight", np.zeros((4, 4), np.uint16))
   assert e.load_tensor("model.layers.3.mlp.down_proj.weight", np.zeros((4, 4), np.uint16)) is False   # other shard: ignored
+
+
+@pytest.mark.parametrize("split,B", [([(0, 3)], 3), ([(0, 1), (2, 3)], 2), ([(0, 0), (1, 2), (3, 3)], 4)])
+def test_requests_in_flight_equal_independent_runs(split, B):
+  """B requests interleaved step by step through the ring (own KV cache each) == B independent single-request runs."""
+  import torch
+  from xotorch_b200.ring import LocalRing
+  shape_name = "tiny-llama-hd64"
+  shape = PRESETS[shape_name]
+  n_gen = 12
+  g = torch.Generator().manual_seed(7)
+  prompts = torch.randint(0, shape.vocab, (B, 11), generator=g).to(torch.int32).numpy()
+  single = LocalRing(_native(shape_name, [(0, shape.n_layers - 1)]))
+  want = np.stack([single.generate(prompts[r:r + 1], n_gen)[0] for r in range(B)])
+  ring = LocalRing(_native(shape_name, split))
+  got, ms = ring.generate_batch(prompts, n_gen)
+  assert np.array_equal(got, want), (got, want)
+  got2, _ = ring.generate_batch(prompts[::-1].copy(), n_gen)     # a second batch on the same engines
+  assert np.array_equal(got2, want[::-1])
+  one, _ = ring.generate(prompts[0:1], n_gen)                    # and back to a single request
+  assert np.array_equal(one, want[0])

@@ -112,8 +112,10 @@ struct xotb200_engine {
   std::multimap<std::string, TensorSlot> slots;   // HF name -> destination(s) (a tied embedding feeds two)
   int tk = 0;                                     // columns per ring stage, fixed per engine
   // request state
-  bf16* kv = nullptr;
+  bf16* kv = nullptr;              // [nreq][local layer][k|v][Hkv][L][hd]
   int L = 0;
+  int nreq = 1, cur_req = 0;       // requests in flight through the ring / request selected for xotb200_forward
+  size_t kv_req_stride = 0;
   float2* rope = nullptr;
   int rope_len = 0;
   // activations / scratch
@@ -252,6 +254,7 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
   a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
+  a.nreq = e->nreq; a.nslots = e->nreq + 1; a.req0 = e->cur_req; a.kv_req_stride = e->kv_req_stride;
   a.src_tokens = e->stage_tokens; a.src_hidden = e->stage_in; a.out_hidden = e->stage_out;
   a.xbuf_bytes = e->mega_xbuf;
   a.dbg = (mode == 0 && e->dbg_step >= 0) ? e->dbg : nullptr; a.dbg_step = e->dbg_step; a.dbg_cta = e->dbg_cta;
@@ -407,8 +410,8 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
     }
     for (int li = 0; li < nl; ++li) {
       const LayerW& w = e->layers[li];
-      bf16* kc = e->kv + ((size_t)li * 2 + 0) * Hkv * e->L * hd;
-      bf16* vc = e->kv + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
+      bf16* kc = e->kv + (size_t)e->cur_req * e->kv_req_stride + ((size_t)li * 2 + 0) * Hkv * e->L * hd;
+      bf16* vc = e->kv + (size_t)e->cur_req * e->kv_req_stride + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
       DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.attn_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
       TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv};
@@ -609,7 +612,7 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   CK(cudaMalloc(&e->bar_counter, 4));
   CK(cudaMalloc(&e->ctl, sizeof(StepCtl)));
   MEMSET_SYNC(e, e->ctl, 0, sizeof(StepCtl));
-  const size_t inbox_bytes = sizeof(InboxHdr) + (size_t)2 * D * 2;
+  const size_t inbox_bytes = sizeof(InboxHdr) + (size_t)INBOX_SLOTS * D * 2;
   CK(cudaMalloc(&e->inbox, inbox_bytes));
   MEMSET_SYNC(e, e->inbox, 0, inbox_bytes);
   CK(cudaMalloc(&e->tokens_log, MAX_RING_STEPS * 4));
@@ -798,18 +801,21 @@ int xotb200_init_synthetic(xotb200_engine* e, uint64_t seed) {
   return 0;
 }
 
-int xotb200_begin_request(xotb200_engine* e, int max_total_len) {
+int xotb200_begin_batch(xotb200_engine* e, int max_total_len, int n_requests) {
   REQUIRE(e && e->start >= 0, "no shard set");
+  REQUIRE(n_requests >= 1 && n_requests <= INBOX_SLOTS - 1, "n_requests must be 1..%d", INBOX_SLOTS - 1);
   REQUIRE(max_total_len > 0 && max_total_len <= e->cfg.max_pos, "max_total_len %d out of range (max_position_embeddings %d)",
           max_total_len, e->cfg.max_pos);
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   const xotb200_model_cfg& c = e->cfg;
   const size_t nl = e->end - e->start + 1;
-  if (max_total_len > e->L) {
+  if (max_total_len > e->L || n_requests != e->nreq) {
     if (e->kv) { CK(cudaFree(e->kv)); e->kv = nullptr; }
-    e->L = max_total_len;
-    CK(cudaMalloc(&e->kv, nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim * 2));
+    e->L = std::max(e->L, max_total_len);
+    e->nreq = n_requests;
+    e->kv_req_stride = nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim;
+    CK(cudaMalloc(&e->kv, (size_t)e->nreq * e->kv_req_stride * 2));
   }
   if (max_total_len > e->rope_len) {
     // RoPE table: theta_j in fp32, angle = fp32(pos * theta_j), cos/sin correctly rounded
@@ -856,10 +862,19 @@ int xotb200_begin_request(xotb200_engine* e, int max_total_len) {
     MEMCPY_SYNC(e, e->d_layers, h.data(), nl * sizeof(LayerDev), cudaMemcpyHostToDevice);
   }
   // reset_caches (llm_utils.py:409-414): zero like torchtune's KVCache.reset
-  CK(cudaMemsetAsync(e->kv, 0, nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim * 2, e->stream));
+  CK(cudaMemsetAsync(e->kv, 0, (size_t)e->nreq * e->kv_req_stride * 2, e->stream));
+  e->cur_req = 0;
   CK(cudaMemsetAsync(e->ctl, 0, sizeof(StepCtl), e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->have_result = false;
+  return 0;
+}
+
+int xotb200_begin_request(xotb200_engine* e, int max_total_len) { return xotb200_begin_batch(e, max_total_len, 1); }
+
+int xotb200_select_request(xotb200_engine* e, int request) {
+  REQUIRE(e && request >= 0 && request < e->nreq, "request index out of range (batch of %d)", e ? e->nreq : 0);
+  e->cur_req = request;
   return 0;
 }
 
@@ -982,9 +997,9 @@ int xotb200_post_to_next(xotb200_engine* e, int step) {
   REQUIRE(e->have_result, "no forward result to post");
   CK(cudaSetDevice(e->device));
   if (e->last)
-    post_kernel<<<1, 256, 0, e->stream>>>(e->next_inbox, nullptr, e->cfg.dim, &e->ctl->token, step);
+    post_kernel<<<1, 256, 0, e->stream>>>(e->next_inbox, nullptr, e->cfg.dim, &e->ctl->token, step, e->nreq + 1);
   else
-    post_kernel<<<1, 256, 0, e->stream>>>(e->next_inbox, e->x, e->cfg.dim, nullptr, step);
+    post_kernel<<<1, 256, 0, e->stream>>>(e->next_inbox, e->x, e->cfg.dim, nullptr, step, e->nreq + 1);
   CK(cudaGetLastError());
   e->launches++;
   CK(cudaStreamSynchronize(e->stream));
@@ -994,7 +1009,9 @@ int xotb200_post_to_next(xotb200_engine* e, int step) {
 int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0) {
   REQUIRE(e && e->start >= 0 && e->next_inbox, "ring not linked");
   REQUIRE(n_steps >= 1 && n_steps <= MAX_RING_STEPS, "n_steps out of range (1..%d)", MAX_RING_STEPS);
-  REQUIRE(e->L > 0 && pos0 + n_steps <= e->L, "KV cache overflow: pos0 %d + steps %d > capacity %d", pos0, n_steps, e->L);
+  REQUIRE(n_steps % e->nreq == 0, "n_steps %d must be a multiple of the %d requests in flight", n_steps, e->nreq);
+  REQUIRE(e->L > 0 && pos0 + n_steps / e->nreq <= e->L, "KV cache overflow: pos0 %d + %d steps per request > capacity %d", pos0,
+          n_steps / e->nreq, e->L);
   if (int rc = xotb200_check_loaded(e)) return rc;
   CK(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;

@@ -25,11 +25,12 @@ struct StepCtl {
 };
 
 // Inbox: lives in the RECEIVER's HBM; written by the previous shard over NVLink (or locally for a 1-shard ring).
+constexpr int INBOX_SLOTS = 9;   // up to 8 requests in flight through a ring + 1
 struct InboxHdr {
-  unsigned int flag_hidden[2];   // == step+1 when hidden[slot] holds the activation of ring step `step`
-  unsigned int flag_token[2];    // == step+1 when token[slot] holds the token id feeding ring step `step`
-  int token[2];
-  int pad[26];                   // header is 128 bytes; bf16 hidden[2][D] follows
+  unsigned int flag_hidden[INBOX_SLOTS];   // == step+1 when hidden[slot] holds the activation of ring step `step`
+  unsigned int flag_token[INBOX_SLOTS];    // == step+1 when token[slot] holds the token id feeding ring step `step`
+  int token[INBOX_SLOTS];
+  int pad[32 - 3 * INBOX_SLOTS];           // header is 128 bytes; bf16 hidden[INBOX_SLOTS][D] follows
 };
 static_assert(sizeof(InboxHdr) == 128, "InboxHdr must be 128 bytes");
 
@@ -117,8 +118,8 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
 // small utility kernels
 // ------------------------------------------------------------------------------------------------------------
 // post a hidden vector / token into the next inbox and release the flag (used once, after prefill)
-__global__ void post_kernel(InboxHdr* next, const bf16* hidden, int D, const int* token, int step) {
-  const int slot = step & 1;
+__global__ void post_kernel(InboxHdr* next, const bf16* hidden, int D, const int* token, int step, int nslots) {
+  const int slot = step % nslots;
   if (hidden) {
     bf16* dst = reinterpret_cast<bf16*>(reinterpret_cast<char*>(next) + sizeof(InboxHdr)) + (size_t)slot * D;
     for (int i = threadIdx.x; i < D; i += blockDim.x) dst[i] = hidden[i];

@@ -69,6 +69,10 @@ struct MegaArgs {
   unsigned int* bar_counter; // grid barrier counter (host zeroes it before every launch)
   int mode;                  // 0 ring, 1 direct
   int n_steps, step0, pos0;
+  int nreq;                  // requests in flight (ring mode): ring step s serves request s % nreq at position pos0 + s / nreq
+  int nslots;                // inbox slots in use = nreq + 1 (a shard is never more than nreq-1 steps ahead of the next one)
+  int req0;                  // direct mode: the request whose KV cache this call works on
+  size_t kv_req_stride;      // elements between the KV caches of consecutive requests
   const int* src_tokens;     // direct, first shard: [n_steps]
   const bf16* src_hidden;    // direct, other shards: [n_steps, D]
   bf16* out_hidden;          // direct, non-last shard: [n_steps, D]

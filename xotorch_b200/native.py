@@ -103,6 +103,13 @@ class NativeShard:
   def begin_request(self, max_total_len: int):
     check(self.lib.xotb200_begin_request(self.h, int(max_total_len)))
 
+  def begin_batch(self, max_total_len: int, n_requests: int):
+    """n_requests independent requests in flight through the ring, one KV cache each"""
+    check(self.lib.xotb200_begin_batch(self.h, int(max_total_len), int(n_requests)))
+
+  def select_request(self, request: int):
+    check(self.lib.xotb200_select_request(self.h, int(request)))
+
   def forward(self, input_data: np.ndarray, pos0: int) -> np.ndarray:
     """ndim==2 int ids [1,S] (first shard) or ndim==3 float32 hidden [1,S,D] -> hidden [1,S,D] f32 or logits [1,V] f32."""
     if input_data.ndim == 2:

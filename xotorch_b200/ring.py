@@ -56,6 +56,37 @@ class LocalRing:
     self._step += n_gen - 1
     return np.concatenate([[first], toks]).astype(np.int32), ms
 
+  def generate_batch(self, prompts: np.ndarray, n_gen: int) -> Tuple[np.ndarray, float]:
+    """B independent requests (prompts [B, S], same length) kept in flight through the ring together: ring step s serves
+    request s % B, so with B >= number of shards no GPU idles.  Returns (ids [B, n_gen], decode ms)."""
+    prompts = np.asarray(prompts, dtype=np.int32)
+    B, S = prompts.shape
+    self._step = (self._step + B - 1) // B * B                 # ring step numbers of a batch start at a multiple of B
+    for e in self.engines:
+      e.begin_batch(S + n_gen + 1, B)
+    first = []
+    for r in range(B):
+      data = prompts[r:r + 1]
+      for e in self.engines:
+        e.select_request(r)
+        data = e.forward(data, 0)
+      first.append(self.engines[-1].last_token())
+      if n_gen > 1:
+        self.engines[-1].post_to_next(self._step + r)          # seeds request r's first ring step
+    if n_gen == 1:
+      return np.array(first, dtype=np.int32).reshape(B, 1), 0.0
+    n_steps = B * (n_gen - 1)
+    for e in self.engines:
+      e.ring_launch(n_steps, self._step, S)
+    toks, ms = None, 0.0
+    for e in self.engines:
+      t, m = e.ring_wait(n_steps)
+      toks = t if t is not None else toks
+      ms = max(ms, m)
+    self._step += n_steps
+    ids = np.concatenate([np.array(first, dtype=np.int32).reshape(B, 1), toks.reshape(n_gen - 1, B).T], axis=1)
+    return ids, ms
+
 
 class DistributedRing:
   """One process per shard (torchrun / torch.distributed): rank r owns shard r of the ring and GPU LOCAL_RANK.
