@@ -31,6 +31,12 @@ class FakeShard:
   def link_next_ipc(self, h): self.linked = h[0]
   def link_next_local(self, other): self.linked = "self"
   def begin_request(self, n): self.calls.append(("begin", n))
+  def begin_batch(self, n, b): self.calls.append(("begin_batch", n, b))
+  def select_request(self, r): self.calls.append(("select", r))
+  def last_token(self): return 1000 + [c[1] for c in self.calls if c[0] == "select"][-1]
+  def post_to_next(self, step): self.calls.append(("post", step))
+  def ring_launch(self, n_steps, step0, pos0): self.calls.append(("launch", n_steps, step0, pos0))
+  def ring_wait(self, n_steps): return (np.arange(n_steps, dtype=np.int32) if self.is_last else None), 1.0
 
   def forward(self, x, pos0):
     self.calls.append(("forward", x.ndim, tuple(x.shape), pos0))
@@ -67,7 +73,10 @@ def _worker(rank, world, port, q):
   tok = int(np.argmax(logits[0])) if native.is_last else 0
   tok = ring._bcast_token(tok)
   ids = ring.api_decode(tok, 5, 8)
-  q.put((rank, native.linked, tok, ids, native.calls))
+  ring.step = 7                                            # a batch must start at a ring step that is a multiple of B
+  n0 = len(native.calls)
+  bids, _ = ring.generate_batch(np.arange(15, dtype=np.int32).reshape(3, 5), 4)
+  q.put((rank, native.linked, tok, ids, native.calls[:n0], native.calls[n0:], None if bids is None else bids.tolist(), ring.step))
   dist.barrier()
   dist.destroy_process_group()
 
@@ -96,10 +105,20 @@ def test_distributed_ring_host_logic(world):
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
-  for rank, linked, tok, ids, calls in res:
+  for rank, linked, tok, ids, calls, bcalls, bids, step in res:
     assert linked == (rank + 1) % world                 # each rank mapped the inbox of the NEXT rank
     assert tok == tok1 and ids == ids1                  # sharded ring == unsharded, on every rank
     fw = [c for c in calls if c[0] == "forward"]
     assert len(fw) == 9 and fw[0][3] == 0 and [c[3] for c in fw[1:]] == list(range(5, 13))
     assert fw[0][1] == (2 if rank == 0 else 3)          # ndim protocol: ids on the first shard, hidden elsewhere
     assert calls[0] == ("begin", 14)
+    # requests in flight: B=3 requests, 4 tokens each -> ring steps 9..17 (7 rounded up to a multiple of 3), 9 steps
+    assert bcalls[0] == ("begin_batch", 5 + 4 + 1, 3) and step == 9 + 9
+    assert [c[1] for c in bcalls if c[0] == "select"] == [0, 1, 2]
+    assert [c for c in bcalls if c[0] == "launch"] == [("launch", 9, 9, 5)]
+    if rank == world - 1:
+      assert [c[1] for c in bcalls if c[0] == "post"] == [9, 10, 11]      # request r seeds ring step step0 + r
+      # ring step s carries request s % 3: ids[r] = [first token of r, steps r, r+3, r+6]
+      assert bids == [[1000 + r, r, r + 3, r + 6] for r in range(3)]
+    else:
+      assert bids is None and not [c for c in bcalls if c[0] == "post"]

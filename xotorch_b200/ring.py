@@ -182,3 +182,37 @@ class DistributedRing:
     toks, ms = self.native.ring_wait(n_steps)
     self.step += n_steps
     return toks, ms
+
+  # -- B requests in flight: ring step s serves request s % B; with B >= world no GPU idles ------------
+  def generate_batch(self, prompts: np.ndarray, n_gen: int) -> Tuple[Optional[np.ndarray], float]:
+    """prompts [B, S] (same on every rank).  Prefill per request through the host-array path, then ONE persistent kernel
+    per rank for B*(n_gen-1) ring steps.  Returns (ids [B, n_gen] on the last rank | None, device ms of this rank)."""
+    prompts = np.asarray(prompts, dtype=np.int32)
+    B, S = prompts.shape
+    self.step = (self.step + B - 1) // B * B
+    self.native.begin_batch(S + n_gen + 1, B)
+    if self.world > 1:
+      self.dist.barrier()                                  # every inbox is reset before anybody posts into one
+    first = []
+    for r in range(B):
+      self.native.select_request(r)
+      self.forward_through_ring(prompts[r:r + 1] if self.first else None, S, 0)
+      if self.last:
+        first.append(self.native.last_token())
+        if n_gen > 1:
+          self.native.post_to_next(self.step + r)
+    n_steps = B * (n_gen - 1)
+    toks, ms = None, 0.0
+    if n_steps:
+      if self.world > 1:
+        self.dist.barrier()
+      self.native.ring_launch(n_steps, self.step, S)
+      toks, ms = self.native.ring_wait(n_steps)
+      self.step += n_steps
+    if not self.last:
+      return None, ms
+    ids = np.array(first, dtype=np.int32).reshape(B, 1)
+    if toks is not None:
+      ids = np.concatenate([ids, toks.reshape(n_gen - 1, B).T], axis=1)
+    return ids, ms
+
