@@ -1,7 +1,7 @@
 """Tensor-core (tcgen05/TMEM/TMA) prefill path — GPU tests through the C ABI.
 1. the GEMM kernel alone against numpy (bf16 inputs, fp32 accumulation, one bf16 rounding);
 2. prefill through the GEMM path vs the CPU oracle and vs the decode-kernel path (both within the bf16 tolerance of
-   tests/test_gpu_parity.py), including prompts longer than one 128-token tile and sharded == unsharded bit-exactness."""
+   tests/test_gpu_parity.py), including prompts longer than one 128-token tile and longer than one 1024-token chunk and sharded == unsharded bit-exactness."""
 import numpy as np
 import pytest
 import torch
@@ -38,7 +38,7 @@ def test_tcgen05_gemm_matches_numpy(S, N, K, tk):
 
 
 @pytest.mark.parametrize("shape_name,n_prompt", [("tiny-llama-hd64", 40), ("tiny-llama-hd128", 131), ("tiny-llama-3.2", 200),
-                                                 ("tiny-llama-hd128-f16", 140)])
+                                                 ("tiny-llama-hd128-f16", 140), ("tiny-llama-hd64", 1100)])
 def test_tc_prefill_matches_oracle_and_decode_kernel_path(shape_name, n_prompt):
   shape = PRESETS[shape_name]
   full = [(0, shape.n_layers - 1)]

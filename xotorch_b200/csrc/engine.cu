@@ -151,6 +151,7 @@ struct xotb200_engine {
   CUtensorMap tm_xn, tm_ao, tm_act;
   std::vector<CUtensorMap> tm_w;   // 4 per local layer (qkv, o, gu, down) + head
   bool tc_ready = false;
+  int tc_cap = 0;                  // token rows the tensor-core scratch buffers currently hold
   unsigned long long* dbg = nullptr;
   int dbg_step = -1, dbg_cta = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -281,11 +282,11 @@ static encode_tiled_fn get_encode_tiled() {
   }
   return fn;
 }
-// activations [128, K] row-major bf16 -> box {64 k, 128 rows}, SWIZZLE_128B
-static int make_tmap_act(CUtensorMap* m, bf16* ptr, int K) {
+// activations [rows, K] row-major bf16 (rows a multiple of 128) -> box {64 k, 128 rows}, SWIZZLE_128B
+static int make_tmap_act(CUtensorMap* m, bf16* ptr, int K, int rows = TC_M) {
   encode_tiled_fn enc = get_encode_tiled();
   REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)TC_M};
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_M};
   const cuuint32_t es[2] = {1, 1};
@@ -329,7 +330,8 @@ static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CU
     CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT)));
     attr_done[key] = true;
   }
-  fn<<<a.N / NT, TC_THREADS, tc_smem_bytes(NT), st>>>(tmA, tmB, a);
+  const int mtiles = epi == TCE_HEAD_LAST ? 1 : (a.S + TC_M - 1) / TC_M - a.mt0;
+  fn<<<dim3(mtiles, a.N / NT), TC_THREADS, tc_smem_bytes(NT), st>>>(tmA, tmB, a);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -343,25 +345,26 @@ static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUten
   return launch_tc_gemm_nt<128>(e, tmA, tmB, a, epi, st);
 }
 
-static int prepare_tc(xotb200_engine* e) {
-  if (e->tc_ready) return 0;
+static int prepare_tc(xotb200_engine* e, int n_tokens) {
   const xotb200_model_cfg& c = e->cfg;
   const size_t D = c.dim, F = c.ffn, qd = (size_t)c.n_heads * c.head_dim, nqkv = (size_t)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
-  if (!e->tc_x) {
-    CK(cudaMalloc(&e->tc_x, TC_M * D * 2));
-    CK(cudaMalloc(&e->tc_xn, TC_M * D * 2));
-    CK(cudaMalloc(&e->tc_qkv, TC_M * nqkv * 2));
-    CK(cudaMalloc(&e->tc_q, TC_M * qd * 2));
-    CK(cudaMalloc(&e->tc_ao, TC_M * qd * 2));
-    CK(cudaMalloc(&e->tc_gu, TC_M * 2 * F * 2));
-    CK(cudaMalloc(&e->tc_act, TC_M * F * 2));
-    MEMSET_SYNC(e, e->tc_xn, 0, TC_M * D * 2);
-    MEMSET_SYNC(e, e->tc_ao, 0, TC_M * qd * 2);
-    MEMSET_SYNC(e, e->tc_act, 0, TC_M * F * 2);
-    if (int rc = make_tmap_act(&e->tm_xn, e->tc_xn, (int)D)) return rc;
-    if (int rc = make_tmap_act(&e->tm_ao, e->tc_ao, (int)qd)) return rc;
-    if (int rc = make_tmap_act(&e->tm_act, e->tc_act, (int)F)) return rc;
+  const int need = (std::min(n_tokens, TC_CHUNK) + TC_M - 1) / TC_M * TC_M;
+  if (need > e->tc_cap) {   // scratch for one chunk of `need` token rows (grown on demand, kept across requests)
+    CK(cudaStreamSynchronize(e->stream));
+    bf16** bufs[] = {&e->tc_x, &e->tc_xn, &e->tc_qkv, &e->tc_q, &e->tc_ao, &e->tc_gu, &e->tc_act};
+    const size_t cols[] = {D, D, nqkv, qd, qd, 2 * F, F};
+    for (int i = 0; i < 7; ++i) {
+      if (*bufs[i]) CK(cudaFree(*bufs[i]));
+      *bufs[i] = nullptr;
+      CK(cudaMalloc(bufs[i], (size_t)need * cols[i] * 2));
+      MEMSET_SYNC(e, *bufs[i], 0, (size_t)need * cols[i] * 2);
+    }
+    e->tc_cap = need;
+    if (int rc = make_tmap_act(&e->tm_xn, e->tc_xn, (int)D, need)) return rc;
+    if (int rc = make_tmap_act(&e->tm_ao, e->tc_ao, (int)qd, need)) return rc;
+    if (int rc = make_tmap_act(&e->tm_act, e->tc_act, (int)F, need)) return rc;
   }
+  if (e->tc_ready) return 0;
   const int nl = e->end - e->start + 1;
   e->tm_w.assign((size_t)4 * nl + 1, CUtensorMap{});
   for (int li = 0; li < nl; ++li) {
@@ -379,28 +382,32 @@ static int prepare_tc(xotb200_engine* e) {
 
 template <int HD>
 static int launch_tc_attn(xotb200_engine* e, int S, int R, bf16* kc, bf16* vc, int pos0, cudaStream_t st) {
-  dim3 grid(S, e->cfg.n_kv_heads);
-  const float scale = 1.0f / sqrtf((float)HD);
-  switch (R) {
-    case 2: DT_LAUNCH(e, (tc_attn_prefill_kernel<HD, 2><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale))); break;
-    case 4: DT_LAUNCH(e, (tc_attn_prefill_kernel<HD, 4><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale))); break;
-    case 8: DT_LAUNCH(e, (tc_attn_prefill_kernel<HD, 8><<<grid, 128, 0, st>>>(e->tc_q, kc, vc, e->tc_ao, e->cfg.n_heads, e->L, pos0, scale))); break;
-    default: set_err("unsupported GQA ratio %d", R); return XOTB200_EINVAL;
+  constexpr int SMEM = (64 + 4 * 64) * HD * 2;          // Q tile + 2 x (K, V) tiles
+  const bool f16 = e->cfg.dtype == XOTB200_DTYPE_F16;
+  auto fn = f16 ? xb::fp::tc_flash_attn_kernel<HD> : xb::bf::tc_flash_attn_kernel<HD>;
+  static std::map<std::pair<int, void*>, bool> attr_done;
+  auto key = std::make_pair(e->device, (void*)fn);
+  if (!attr_done.count(key)) {
+    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done[key] = true;
   }
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  fn<<<dim3((S + 63) / 64, e->cfg.n_heads), 128, SMEM, st>>>(e->tc_q, kc, vc, e->tc_ao, S, e->cfg.n_heads, R, e->L, pos0, scale_log2);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
 }
 
-// Prefill n_tokens positions starting at pos0 on the tensor cores, in tiles of 128 tokens.  Inputs: stage_tokens /
+// Prefill n_tokens positions starting at pos0 on the tensor cores, in chunks of up to TC_CHUNK tokens (layer-major
+// inside a chunk, so a chunk streams the shard's weights once).  Inputs: stage_tokens /
 // stage_in; outputs: stage_out (non-last shard) or logits + ctl->token of the last position (last shard).
 static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st) {
-  if (int rc = prepare_tc(e)) return rc;
+  if (int rc = prepare_tc(e, n_tokens)) return rc;
   const xotb200_model_cfg& c = e->cfg;
   const int D = c.dim, F = c.ffn, Hq = c.n_heads, Hkv = c.n_kv_heads, hd = c.head_dim;
   const int qd = Hq * hd, nqkv = (Hq + 2 * Hkv) * hd, nl = e->end - e->start + 1;
-  for (int m0 = 0; m0 < n_tokens; m0 += TC_M) {
-    const int S = std::min(TC_M, n_tokens - m0);
+  for (int m0 = 0; m0 < n_tokens; m0 += TC_CHUNK) {
+    const int S = std::min(TC_CHUNK, n_tokens - m0);
     if (e->first) {
       tc_gather_kernel<<<S, 128, 0, st>>>(e->stage_tokens + m0, e->embed, e->tc_x, D);
       CK(cudaGetLastError());
@@ -414,30 +421,31 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
       bf16* vc = e->kv + (size_t)e->cur_req * e->kv_req_stride + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
       DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.attn_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
-      TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv};
+      TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv, 0};
       if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 0], g, TCE_STORE, st)) return rc;
       DT_LAUNCH(e, (tc_rope_kv_kernel<<<S, 256, 0, st>>>(e->tc_qkv, e->tc_q, kc, vc, e->rope, Hq, Hkv, hd, e->L, pos0 + m0)));
       CK(cudaGetLastError());
       if (int rc = (hd == 128 ? launch_tc_attn<128>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)
                               : launch_tc_attn<64>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)))
         return rc;
-      TcGemmArgs o{S, D, qd, e->tk, e->tc_x, nullptr, D};
+      TcGemmArgs o{S, D, qd, e->tk, e->tc_x, nullptr, D, 0};
       if (int rc = launch_tc_gemm(e, e->tm_ao, e->tm_w[4 * li + 1], o, TCE_RESID, st)) return rc;
       DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.mlp_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
-      TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F};
+      TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F, 0};
       if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 2], u, TCE_STORE, st)) return rc;
       DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F)));
       CK(cudaGetLastError());
-      TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D};
+      TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D, 0};
       if (int rc = launch_tc_gemm(e, e->tm_act, e->tm_w[4 * li + 3], d, TCE_RESID, st)) return rc;
       e->launches += 4;
     }
     if (e->last) {
       if (m0 + S == n_tokens) {   // logits of the last position only (sharded_inference_engine.py:365-368)
-        DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, e->final_norm, e->tc_xn, D, c.norm_eps)));
+        const int mt_last = (S - 1) / TC_M, r0 = mt_last * TC_M;   // only the tile holding the last position
+        DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S - r0, 256, 0, st>>>(e->tc_x + (size_t)r0 * D, e->final_norm, e->tc_xn + (size_t)r0 * D, D, c.norm_eps)));
         CK(cudaGetLastError());
-        TcGemmArgs h{S, c.vocab, D, e->tk, nullptr, e->logits, 0};
+        TcGemmArgs h{S, c.vocab, D, e->tk, nullptr, e->logits, 0, mt_last};
         if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * nl], h, TCE_HEAD_LAST, st)) return rc;
         tc_argmax_kernel<<<1, 1024, 0, st>>>(e->logits, c.vocab, e->ctl);
         CK(cudaGetLastError());
@@ -448,7 +456,7 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
     }
   }
   // the residual stream of the last position is what xotb200_post_to_next hands to the next shard
-  CK(cudaMemcpyAsync(e->x, e->tc_x + (size_t)((n_tokens - 1) % TC_M) * D, (size_t)D * 2, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(e->x, e->tc_x + (size_t)((n_tokens - 1) % TC_CHUNK) * D, (size_t)D * 2, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -1083,7 +1091,7 @@ int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16
   int rc = make_tmap_act(&tA, dA, K);
   if (!rc) rc = make_tmap_w(&tB, dW, N, K, tk, tc_nt(N));
   if (!rc) {
-    TcGemmArgs g{S, N, K, tk, dO, nullptr, N};
+    TcGemmArgs g{S, N, K, tk, dO, nullptr, N, 0};
     rc = launch_tc_gemm(e, tA, tB, g, TCE_STORE, e->stream);
   }
   cudaError_t er = cudaStreamSynchronize(e->stream);

@@ -25,12 +25,16 @@ constexpr int TC_THREADS = 256;  // warp 0 TMA producer, warp 1 MMA issuer, warp
 
 enum { TCE_STORE = 0, TCE_RESID = 1, TCE_HEAD_LAST = 2 };
 
+constexpr int TC_CHUNK = 1024;   // tokens per prefill pass: every weight tile is fetched from HBM once per chunk and reused
+                                 // by the chunk's 128-token tiles out of L2 (grid x = token tile, so they run together)
+
 struct TcGemmArgs {
-  int S;            // valid token rows of this tile (<= 128)
+  int S;            // valid token rows of the chunk (grid.x = ceil(S/128) token tiles; HEAD_LAST: only the last tile)
   int N, K, tk;     // output features, reduction length, K-panel width of the weight layout
   bf16* out;        // STORE: [S, ld] bf16;  RESID: residual stream x [S, ld], updated in place
   float* logits;    // HEAD_LAST: [N] fp32, row S-1 only (bf16-valued)
   int ld;           // row stride of `out` in elements
+  int mt0;          // first token tile of this launch (0, or the last tile for HEAD_LAST)
 };
 
 __host__ __device__ constexpr int tc_stage_bytes(int nt) { return TC_M * TC_BK * 2 + nt * TC_BK * 2; }
