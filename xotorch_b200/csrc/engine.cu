@@ -149,8 +149,7 @@ struct xotb200_engine {
   int prefill_mode = 0;            // 0 auto (TC when n_tokens >= 8), 1 always the decode kernel, 2 always TC
   bf16 *tc_x = nullptr, *tc_xn = nullptr, *tc_qkv = nullptr, *tc_q = nullptr, *tc_ao = nullptr, *tc_gu = nullptr, *tc_act = nullptr;
   CUtensorMap tm_xn, tm_ao, tm_act;
-  std::vector<CUtensorMap> tm_w;   // 4 per local layer (qkv, o, gu, down) + head
-  bool tc_ready = false;
+  std::map<int, std::vector<CUtensorMap>> tm_w;   // per N-tile width: 4 per local layer (qkv, o, gu, down) + head
   int tc_cap = 0;                  // token rows the tensor-core scratch buffers currently hold
   unsigned long long* dbg = nullptr;
   int dbg_step = -1, dbg_cta = 0;
@@ -309,40 +308,76 @@ static int make_tmap_w(CUtensorMap* m, const bf16* ptr, int N, int K, int tk, in
   REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights N=%d K=%d tk=%d) failed: %d", N, K, tk, (int)r);
   return 0;
 }
-static int tc_nt(int N) {
-  static int small = getenv("XOTB200_TC_NT_SMALL") ? atoi(getenv("XOTB200_TC_NT_SMALL")) : 64;   // tuning hook (32 | 64)
-  return N <= 8192 ? small : 128;
+// GEMM tile configuration {N tile, ring stages}.  One 128-token tile (S <= 128) is HBM-bound: many CTAs, deep rings.
+// Several token tiles are tensor-bound: measured on B200 (8B shape, 1024 / 4096 tokens, whole prefill): 256x4 16.2 / 80 ms,
+// 128x3 (two CTAs per SM, epilogue of one under the MMAs of the other) 17.4 / 88, 128x6 21.1 / 99, 64x8 34.7 / 153.  XOTB200_TC_SMALL / XOTB200_TC_BIG = "nt,ns" override (tuning hook).
+struct TcCfg { int nt, ns; };
+static TcCfg tc_env(const char* name, TcCfg dflt) {
+  const char* v = getenv(name);
+  TcCfg c = dflt;
+  if (v && sscanf(v, "%d,%d", &c.nt, &c.ns) != 2) c = dflt;
+  return c;
 }
+static TcCfg tc_cfg(int N, int S) {
+  static const TcCfg small = tc_env("XOTB200_TC_SMALL", {64, 8}), big = tc_env("XOTB200_TC_BIG", {256, 4});
+  TcCfg c = S > TC_M ? big : (N <= 8192 ? small : TcCfg{128, 6});
+  if (N % c.nt != 0 && S > TC_M && N % 128 == 0) c = {128, 3};
+  if (N % c.nt != 0) c = {64, 8};
+  return c;
+}
+static int tc_nt(int N) { return tc_cfg(N, 1).nt; }
 
-template <int NT>
+template <int NT, int NS>
 static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
                              cudaStream_t st) {
   void (*fn)(CUtensorMap, CUtensorMap, TcGemmArgs) = nullptr;
   const bool f16 = e->cfg.dtype == XOTB200_DTYPE_F16;
   switch (epi) {
-    case TCE_STORE: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_STORE> : xb::bf::tc_gemm_kernel<NT, TCE_STORE>; break;
-    case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_RESID> : xb::bf::tc_gemm_kernel<NT, TCE_RESID>; break;
-    default: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_HEAD_LAST> : xb::bf::tc_gemm_kernel<NT, TCE_HEAD_LAST>; break;
+    case TCE_STORE: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_STORE, NS> : xb::bf::tc_gemm_kernel<NT, TCE_STORE, NS>; break;
+    case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_RESID, NS> : xb::bf::tc_gemm_kernel<NT, TCE_RESID, NS>; break;
+    default: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_HEAD_LAST, NS> : xb::bf::tc_gemm_kernel<NT, TCE_HEAD_LAST, NS>; break;
   }
   static std::map<std::pair<int, void*>, bool> attr_done;
   auto key = std::make_pair(e->device, (void*)fn);
   if (!attr_done.count(key)) {
-    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT)));
+    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT, NS)));
     attr_done[key] = true;
   }
   const int mtiles = epi == TCE_HEAD_LAST ? 1 : (a.S + TC_M - 1) / TC_M - a.mt0;
-  fn<<<dim3(mtiles, a.N / NT), TC_THREADS, tc_smem_bytes(NT), st>>>(tmA, tmB, a);
+  fn<<<dim3(mtiles, a.N / NT), TC_THREADS, tc_smem_bytes(NT, NS), st>>>(tmA, tmB, a);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
 }
-static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
+static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi, TcCfg c,
                           cudaStream_t st) {
-  const int nt = tc_nt(a.N);
-  REQUIRE(a.N % nt == 0 && a.K % TC_BK == 0, "tensor-core GEMM needs N %% %d == 0 and K %% 64 == 0 (N=%d K=%d)", nt, a.N, a.K);
-  if (nt == 32) return launch_tc_gemm_nt<32>(e, tmA, tmB, a, epi, st);
-  if (nt == 64) return launch_tc_gemm_nt<64>(e, tmA, tmB, a, epi, st);
-  return launch_tc_gemm_nt<128>(e, tmA, tmB, a, epi, st);
+  REQUIRE(a.N % c.nt == 0 && a.K % TC_BK == 0, "tensor-core GEMM needs N %% %d == 0 and K %% 64 == 0 (N=%d K=%d)", c.nt, a.N, a.K);
+#define TC_CASE(NT_, NS_) if (c.nt == NT_ && c.ns == NS_) return launch_tc_gemm_nt<NT_, NS_>(e, tmA, tmB, a, epi, st)
+  TC_CASE(32, 8); TC_CASE(64, 8); TC_CASE(64, 4); TC_CASE(128, 6); TC_CASE(128, 3); TC_CASE(256, 4); TC_CASE(256, 2);
+#undef TC_CASE
+  set_err("no tensor-core GEMM instantiation for tile %d x %d stages", c.nt, c.ns);
+  return XOTB200_EINVAL;
+}
+
+// weight tensor maps for N-tile width nt: 4 per local layer (qkv, o, gu, down) + head; built on first use of that width
+static int ensure_tm_w(xotb200_engine* e, int nt) {
+  if (e->tm_w.count(nt)) return 0;
+  const xotb200_model_cfg& c = e->cfg;
+  const int D = c.dim, F = c.ffn, qd = c.n_heads * c.head_dim, nqkv = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  const int nl = e->end - e->start + 1;
+  std::vector<CUtensorMap> v((size_t)4 * nl + 1, CUtensorMap{});
+  auto mk = [&](CUtensorMap* m, const bf16* w, int N, int K) { return N % nt ? 0 : make_tmap_w(m, w, N, K, e->tk, nt); };
+  for (int li = 0; li < nl; ++li) {
+    const LayerW& w = e->layers[li];
+    if (int rc = mk(&v[4 * li + 0], w.wqkv, nqkv, D)) return rc;
+    if (int rc = mk(&v[4 * li + 1], w.wo, D, qd)) return rc;
+    if (int rc = mk(&v[4 * li + 2], w.wgu, 2 * F, D)) return rc;
+    if (int rc = mk(&v[4 * li + 3], w.wdown, D, F)) return rc;
+  }
+  if (e->last)
+    if (int rc = mk(&v[4 * nl], e->lm_head, c.vocab, D)) return rc;
+  e->tm_w[nt] = std::move(v);
+  return 0;
 }
 
 static int prepare_tc(xotb200_engine* e, int n_tokens) {
@@ -364,20 +399,14 @@ static int prepare_tc(xotb200_engine* e, int n_tokens) {
     if (int rc = make_tmap_act(&e->tm_ao, e->tc_ao, (int)qd, need)) return rc;
     if (int rc = make_tmap_act(&e->tm_act, e->tc_act, (int)F, need)) return rc;
   }
-  if (e->tc_ready) return 0;
-  const int nl = e->end - e->start + 1;
-  e->tm_w.assign((size_t)4 * nl + 1, CUtensorMap{});
-  for (int li = 0; li < nl; ++li) {
-    const LayerW& w = e->layers[li];
-    if (int rc = make_tmap_w(&e->tm_w[4 * li + 0], w.wqkv, (int)nqkv, (int)D, e->tk, tc_nt((int)nqkv))) return rc;
-    if (int rc = make_tmap_w(&e->tm_w[4 * li + 1], w.wo, (int)D, (int)qd, e->tk, tc_nt((int)D))) return rc;
-    if (int rc = make_tmap_w(&e->tm_w[4 * li + 2], w.wgu, (int)(2 * F), (int)D, e->tk, tc_nt((int)(2 * F)))) return rc;
-    if (int rc = make_tmap_w(&e->tm_w[4 * li + 3], w.wdown, (int)D, (int)F, e->tk, tc_nt((int)D))) return rc;
-  }
-  if (e->last)
-    if (int rc = make_tmap_w(&e->tm_w[4 * nl], e->lm_head, c.vocab, (int)D, e->tk, tc_nt(c.vocab))) return rc;
-  e->tc_ready = true;
   return 0;
+}
+
+// one GEMM of the prefill: weight `widx` of the shard (see ensure_tm_w), tile configuration from (N, tokens in flight)
+static int tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, int widx, const TcGemmArgs& a, int epi, cudaStream_t st) {
+  const TcCfg c = tc_cfg(a.N, epi == TCE_HEAD_LAST ? 1 : a.S);
+  if (int rc = ensure_tm_w(e, c.nt)) return rc;
+  return launch_tc_gemm(e, tmA, e->tm_w[c.nt][widx], a, epi, c, st);
 }
 
 template <int HD>
@@ -422,22 +451,22 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
       DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.attn_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
       TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv, 0};
-      if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 0], g, TCE_STORE, st)) return rc;
+      if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 0, g, TCE_STORE, st)) return rc;
       DT_LAUNCH(e, (tc_rope_kv_kernel<<<S, 256, 0, st>>>(e->tc_qkv, e->tc_q, kc, vc, e->rope, Hq, Hkv, hd, e->L, pos0 + m0)));
       CK(cudaGetLastError());
       if (int rc = (hd == 128 ? launch_tc_attn<128>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)
                               : launch_tc_attn<64>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)))
         return rc;
       TcGemmArgs o{S, D, qd, e->tk, e->tc_x, nullptr, D, 0};
-      if (int rc = launch_tc_gemm(e, e->tm_ao, e->tm_w[4 * li + 1], o, TCE_RESID, st)) return rc;
+      if (int rc = tc_gemm(e, e->tm_ao, 4 * li + 1, o, TCE_RESID, st)) return rc;
       DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.mlp_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
       TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F, 0};
-      if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * li + 2], u, TCE_STORE, st)) return rc;
+      if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 2, u, TCE_STORE, st)) return rc;
       DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F)));
       CK(cudaGetLastError());
       TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D, 0};
-      if (int rc = launch_tc_gemm(e, e->tm_act, e->tm_w[4 * li + 3], d, TCE_RESID, st)) return rc;
+      if (int rc = tc_gemm(e, e->tm_act, 4 * li + 3, d, TCE_RESID, st)) return rc;
       e->launches += 4;
     }
     if (e->last) {
@@ -446,7 +475,7 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
         DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S - r0, 256, 0, st>>>(e->tc_x + (size_t)r0 * D, e->final_norm, e->tc_xn + (size_t)r0 * D, D, c.norm_eps)));
         CK(cudaGetLastError());
         TcGemmArgs h{S, c.vocab, D, e->tk, nullptr, e->logits, 0, mt_last};
-        if (int rc = launch_tc_gemm(e, e->tm_xn, e->tm_w[4 * nl], h, TCE_HEAD_LAST, st)) return rc;
+        if (int rc = tc_gemm(e, e->tm_xn, 4 * nl, h, TCE_HEAD_LAST, st)) return rc;
         tc_argmax_kernel<<<1, 1024, 0, st>>>(e->logits, c.vocab, e->ctl);
         CK(cudaGetLastError());
         e->launches += 2;
@@ -543,7 +572,6 @@ static void free_shard(xotb200_engine* e) {
   e->slots.clear();
   e->mega = nullptr;
   e->tm_w.clear();
-  e->tc_ready = false;
   e->embed = e->final_norm = e->lm_head = nullptr;
   e->start = e->end = -1;
   e->L = 0;
@@ -1092,7 +1120,7 @@ int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16
   if (!rc) rc = make_tmap_w(&tB, dW, N, K, tk, tc_nt(N));
   if (!rc) {
     TcGemmArgs g{S, N, K, tk, dO, nullptr, N, 0};
-    rc = launch_tc_gemm(e, tA, tB, g, TCE_STORE, e->stream);
+    rc = launch_tc_gemm(e, tA, tB, g, TCE_STORE, tc_cfg(N, S), e->stream);
   }
   cudaError_t er = cudaStreamSynchronize(e->stream);
   if (!rc && er == cudaSuccess) {

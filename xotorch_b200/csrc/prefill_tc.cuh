@@ -38,8 +38,9 @@ struct TcGemmArgs {
 };
 
 __host__ __device__ constexpr int tc_stage_bytes(int nt) { return TC_M * TC_BK * 2 + nt * TC_BK * 2; }
-__host__ __device__ constexpr int tc_nstage(int nt) { return nt <= 64 ? 8 : 6; }
-__host__ __device__ constexpr int tc_smem_bytes(int nt) { return tc_nstage(nt) * tc_stage_bytes(nt) + 1024 + 256; }
+__host__ __device__ constexpr int tc_smem_bytes(int nt, int ns) { return ns * tc_stage_bytes(nt) + 1024 + 256; }
+// CTAs per SM the launch bounds ask for: two when two rings fit, so one CTA's TMEM->global epilogue overlaps the other's MMAs
+__host__ __device__ constexpr int tc_occupancy(int nt, int ns) { return 2 * tc_smem_bytes(nt, ns) <= 226 * 1024 && 2 * nt <= 512 ? 2 : 1; }
 
 // ---- PTX wrappers (forms as in CUTLASS cute/arch/{copy_sm90_tma,copy_sm100,mma_sm100_umma,tmem_allocator_sm100}.hpp) ----
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
