@@ -55,6 +55,8 @@ typedef struct xotb200_model_cfg {
   float rope_low_freq_factor;
   float rope_high_freq_factor;
   int32_t rope_old_context_len;
+  int32_t n_experts;        /* num_local_experts: Mixtral-style sparse MoE MLP, 2..8 (0 = dense SwiGLU MLP)   */
+  int32_t experts_per_tok;  /* num_experts_per_tok: must be 2 when n_experts > 0                                */
 } xotb200_model_cfg;
 
 typedef struct xotb200_engine xotb200_engine;
@@ -139,6 +141,10 @@ int xotb200_set_prefill_mode(xotb200_engine* e, int mode);
 /* Unit-test hook for the tensor-core GEMM: out[S,N] (bf16 bits) = A[S,K] * W[N,K]^T with fp32 accumulation, W re-laid out
  * as K-panels of width tk exactly like a model weight.  S <= 128. */
 int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16, int S, int N, int K, int tk, void* out_bf16);
+/* Sparse-MoE shards: the experts the router chose for request 0 at positions [0, n_positions) of the open request,
+ * out[pos * n_local_layers + local_layer] = lower expert | higher expert << 8 (-1 = position not run).  Parity tests use it
+ * to tell a routing near-tie (a discrete, legitimately implementation-dependent choice) from an arithmetic error. */
+int xotb200_debug_routing(xotb200_engine* e, int32_t* out, int n_positions);
 /* Per-op device timeline of CTA `cta` at ring step `step` (-1 disables): for op i the four globaltimer stamps
  * [prologue start, tiles start, tiles done, barrier exit] at out[4*i..4*i+3].  Call once to arm (out may be NULL),
  * run the ring, call again to read. */

@@ -86,6 +86,8 @@ def model_config_from_hf(base: dict) -> dict:
     "hidden_act": base.get("hidden_act", "silu"),
     "torch_dtype": _DTYPES.get(base.get("torch_dtype", "bfloat16"), torch.bfloat16),
     "tie_word_embeddings": bool(base.get("tie_word_embeddings", False)),
+    "num_experts": int(base.get("num_local_experts") or 0),       # Mixtral-style sparse MoE MLP (0 = dense)
+    "experts_per_tok": int(base.get("num_experts_per_tok") or 0),
   }
   rs = cfg["rope_scaling"]
   if rs is not None:
@@ -218,8 +220,15 @@ class RefShardModel:
         "v": g(p + "self_attn.v_proj.weight"),
         "o": g(p + "self_attn.o_proj.weight"),
         "mlp_norm": g(p + "post_attention_layernorm.weight"),
-        "w1": g(p + "mlp.gate_proj.weight"), "w2": g(p + "mlp.down_proj.weight"), "w3": g(p + "mlp.up_proj.weight"),
       }
+      if c.get("num_experts", 0):
+        m = p + "block_sparse_moe."
+        self.layers[i]["router"] = g(m + "gate.weight")
+        self.layers[i]["experts"] = [(g(m + f"experts.{e}.w1.weight"), g(m + f"experts.{e}.w2.weight"), g(m + f"experts.{e}.w3.weight"))
+                                     for e in range(c["num_experts"])]
+      else:
+        self.layers[i].update({"w1": g(p + "mlp.gate_proj.weight"), "w2": g(p + "mlp.down_proj.weight"),
+                               "w3": g(p + "mlp.up_proj.weight")})
     # B6: the reference allocates embedding + head on every shard; only first/last need them.
     self.tok_embeddings = g("model.embed_tokens.weight") if shard.is_first_layer() else None
     if shard.is_last_layer():
@@ -275,8 +284,56 @@ class RefShardModel:
     xn = rms_norm(h, L["sa_norm"], eps, self.norm_variant)
     h = self._attention(i, xn, mask, input_pos) + h
     xm = rms_norm(h, L["mlp_norm"], eps, self.norm_variant)
+    if "router" in L:
+      return h + self._moe(L, xm, i, input_pos)
     mlp = F.linear(F.silu(F.linear(xm, L["w1"])) * F.linear(xm, L["w3"]), L["w2"])
     return h + mlp
+
+  # Routing is a DISCRETE choice on bf16 router logits: two correct implementations whose activations differ by one bf16 ulp
+  # can pick different experts when the 2nd and 3rd logit are (nearly) tied.  For parity tests the choice of another
+  # implementation can be imposed (`forced_routes[(layer, position)] = (lo, hi)`); `route_log` then records this oracle's own
+  # choice and how far (in router-logit units) the imposed pair is from being its own — a test asserts that is ~1 ulp.
+  forced_routes: Optional[dict] = None
+  route_log: Optional[list] = None
+
+  def _moe(self, L: dict, xm: torch.Tensor, layer: int = -1, input_pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Mixtral sparse-MoE MLP.  The reference has no MoE path (its `MOELayer`, llm_utils.py:502-590, is an unused stub:
+    SURVEY.md §0.10), so this restates the third-party algorithm the config names: HF transformers 5.5.0
+    models/mixtral/modeling_mixtral.py:101-116 (MixtralTopKRouter: linear -> fp32 softmax -> top-k -> renormalise) and
+    :74-98 (MixtralExperts: per expert in ascending index, down(silu(gate x) * up x) * fp32 routing weight -> model dtype ->
+    index_add_ into a model-dtype accumulator).  One deliberate pin: torch.topk leaves the order of EQUAL values
+    unspecified; here (and in the CUDA kernel) ties go to the lower expert index."""
+    b, s, D = xm.shape
+    T = xm.reshape(-1, D)
+    k = self.cfg["experts_per_tok"]
+    probs = F.softmax(F.linear(T, L["router"]).float(), dim=-1)
+    order = torch.sort(probs, dim=-1, descending=True, stable=True)
+    top_v, top_i = order.values[:, :k], order.indices[:, :k]
+    if self.forced_routes is not None or self.route_log is not None:
+      logits = F.linear(T, L["router"]).float()
+      pos_list = [int(p) for p in input_pos.reshape(-1)]
+      top_i = top_i.clone()
+      for t, pos in enumerate(pos_list):
+        own = sorted(int(x) for x in top_i[t])
+        used = own
+        if self.forced_routes is not None and (layer, pos) in self.forced_routes:
+          used = sorted(int(x) for x in self.forced_routes[(layer, pos)])
+          top_i[t] = torch.tensor(used)
+        if self.route_log is not None:
+          thr = float(order.values[t, k - 1].log() - order.values[t, 0].log() + logits[t].max())   # own k-th largest logit
+          self.route_log.append((layer, pos, tuple(own), tuple(used), max(0.0, thr - float(logits[t, used].min()))))
+      top_v = torch.gather(probs, 1, top_i)
+    top_v = top_v / top_v.sum(dim=-1, keepdim=True)
+    final = torch.zeros_like(T)
+    for e, (w1, w2, w3) in enumerate(L["experts"]):
+      tok, slot = torch.where(top_i == e)
+      if tok.numel() == 0:
+        continue
+      cur = T[tok]
+      cur = F.linear(F.silu(F.linear(cur, w1)) * F.linear(cur, w3), w2)
+      cur = cur * top_v[tok, slot, None]                  # fp32 weight: the product is fp32 ...
+      final.index_add_(0, tok, cur.to(final.dtype))       # ... rounded to the model dtype, accumulated in the model dtype
+    return final.view(b, s, D)
 
   @torch.inference_mode()
   def forward(self, tokens: Optional[torch.Tensor], *, mask: torch.Tensor, input_pos: torch.Tensor,

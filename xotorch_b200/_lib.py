@@ -24,6 +24,7 @@ class ModelCfg(C.Structure):
     ("rope_theta", C.c_float), ("norm_eps", C.c_float), ("tie_embeddings", C.c_int32), ("dtype", C.c_int32),
     ("rope_kind", C.c_int32), ("rope_factor", C.c_float), ("rope_low_freq_factor", C.c_float),
     ("rope_high_freq_factor", C.c_float), ("rope_old_context_len", C.c_int32),
+    ("n_experts", C.c_int32), ("experts_per_tok", C.c_int32),
   ]
 
 
@@ -60,6 +61,7 @@ _SIGS = {
   "xotb200_set_cta_limit": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_set_prefill_mode": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+  "xotb200_debug_routing": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int]),
   "xotb200_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
   "xotb200_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
   "xotb200_weight_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

@@ -97,7 +97,8 @@ struct TensorSlot {
 };
 
 struct LayerW {
-  bf16 *attn_norm, *wqkv, *wo, *mlp_norm, *wgu, *wdown;
+  bf16 *attn_norm, *wqkv, *wo, *mlp_norm, *wgu, *wdown;   // MoE: wgu / wdown hold the E experts back to back
+  bf16* router;                                           // MoE: [E, D] row-major
 };
 
 struct xotb200_engine {
@@ -131,6 +132,7 @@ struct xotb200_engine {
   InboxHdr* next_inbox = nullptr;
   bool next_ipc = false;
   int* tokens_log = nullptr;
+  int* route_log = nullptr;         // sparse MoE: experts chosen per (position, local layer) of request 0
   unsigned long long *t_in = nullptr, *t_out = nullptr;
   // staging for the host-buffer API
   int stage_cap = 0;
@@ -179,27 +181,34 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 typedef void (*mega_fn)(const MegaArgs);
 
 #define PICK_MEGA_NS(NSP)                                                                                   \
-  template <int TK, int HD, int NS>                                                                          \
+  template <int TK, int HD, int NS, bool MOE>                                                                \
   static mega_fn pick_mega_r_##NSP(int R) {                                                                  \
     switch (R) {                                                                                             \
-      case 2: return xb::NSP::shard_step_kernel<TK, HD, 2, NS>;                                              \
-      case 4: return xb::NSP::shard_step_kernel<TK, HD, 4, NS>;                                              \
-      case 8: return xb::NSP::shard_step_kernel<TK, HD, 8, NS>;                                              \
+      case 2: return xb::NSP::shard_step_kernel<TK, HD, 2, NS, MOE>;                                         \
+      case 4: return xb::NSP::shard_step_kernel<TK, HD, 4, NS, MOE>;                                         \
+      case 8: return xb::NSP::shard_step_kernel<TK, HD, 8, NS, MOE>;                                         \
       default: return nullptr;                                                                               \
     }                                                                                                        \
   }                                                                                                          \
-  static mega_fn pick_mega_##NSP(int tk, int hd, int R, int ns) {                                            \
-    if (tk == 2048 && hd == 128 && ns == 12) return pick_mega_r_##NSP<2048, 128, 12>(R);                    \
-    if (tk == 2048 && hd == 64 && ns == 12) return pick_mega_r_##NSP<2048, 64, 12>(R);                      \
-    if (tk == 2048 && hd == 128 && ns == 8) return pick_mega_r_##NSP<2048, 128, 8>(R); /* very wide (70B) */ \
-    if (tk == 512 && hd == 128 && ns == 12) return pick_mega_r_##NSP<512, 128, 12>(R);                      \
-    if (tk == 512 && hd == 64 && ns == 12) return pick_mega_r_##NSP<512, 64, 12>(R);                        \
+  static mega_fn pick_mega_##NSP(int tk, int hd, int R, int ns, bool moe) {                                  \
+    if (moe) { /* sparse MoE: 2F activations -> 8-stage ring at Mixtral sizes, 12 at the tiny parity shapes */ \
+      if (tk == 2048 && hd == 128 && ns == 8) return pick_mega_r_##NSP<2048, 128, 8, true>(R);              \
+      if (tk == 2048 && hd == 128 && ns == 12) return pick_mega_r_##NSP<2048, 128, 12, true>(R);            \
+      if (tk == 512 && hd == 128 && ns == 12) return pick_mega_r_##NSP<512, 128, 12, true>(R);              \
+      if (tk == 512 && hd == 64 && ns == 12) return pick_mega_r_##NSP<512, 64, 12, true>(R);                \
+      return nullptr;                                                                                        \
+    }                                                                                                        \
+    if (tk == 2048 && hd == 128 && ns == 12) return pick_mega_r_##NSP<2048, 128, 12, false>(R);             \
+    if (tk == 2048 && hd == 64 && ns == 12) return pick_mega_r_##NSP<2048, 64, 12, false>(R);               \
+    if (tk == 2048 && hd == 128 && ns == 8) return pick_mega_r_##NSP<2048, 128, 8, false>(R); /* very wide (70B) */ \
+    if (tk == 512 && hd == 128 && ns == 12) return pick_mega_r_##NSP<512, 128, 12, false>(R);               \
+    if (tk == 512 && hd == 64 && ns == 12) return pick_mega_r_##NSP<512, 64, 12, false>(R);                 \
     return nullptr;                                                                                          \
   }
 PICK_MEGA_NS(bf)
 PICK_MEGA_NS(fp)
-static mega_fn pick_mega(int tk, int hd, int R, int ns, int dtype) {
-  return dtype == XOTB200_DTYPE_F16 ? pick_mega_fp(tk, hd, R, ns) : pick_mega_bf(tk, hd, R, ns);
+static mega_fn pick_mega(int tk, int hd, int R, int ns, int dtype, bool moe) {
+  return dtype == XOTB200_DTYPE_F16 ? pick_mega_fp(tk, hd, R, ns, moe) : pick_mega_bf(tk, hd, R, ns, moe);
 }
 
 static const size_t SMEM_BUDGET = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
@@ -212,15 +221,17 @@ static int prepare_mega(xotb200_engine* e) {
   const int tk = e->tk;
   REQUIRE(tk == 2048 || tk == 512, "no shard set");
   const int R = c.n_heads / c.n_kv_heads;
-  const size_t kmax = (size_t)std::max(std::max(c.dim, c.ffn), qdim);
+  const int grid0 = e->cta_limit > 0 ? std::min(e->sm_count, e->cta_limit) : e->sm_count;
+  const size_t moe_stash = c.n_experts > 0 ? align_up(((size_t)c.dim / 2 + grid0 - 1) / grid0 * 8, 16) : 0;   // float2 per row pair of a CTA
+  const size_t kmax = (size_t)std::max(std::max(c.dim, c.ffn * (c.n_experts > 0 ? 2 : 1)), qdim);
   const size_t attn_scratch = ((size_t)NCW * R * 2 + (size_t)NCW * R * c.head_dim) * 4;
   const size_t xbuf = align_up(std::max(kmax * 2, attn_scratch), 128);
   const size_t fixed = xbuf + (size_t)(2 * mk_nstage(tk) + 2 * MK_NSLOT) * 8 + (size_t)MK_NSLOT * NCW * 8 * 4 + 128 + 128 +
-                       (size_t)c.n_layers * sizeof(LayerDev) + 2048 /* static __shared__ */;
+                       (size_t)c.n_layers * sizeof(LayerDev) + moe_stash + 2048 /* static __shared__ */;
   REQUIRE(fixed + 4 * (size_t)mk_stage_bytes(tk) <= SMEM_BUDGET, "activation width %zu too large for a 4-stage ring", kmax);
   const int nstage = (SMEM_BUDGET - fixed) / mk_stage_bytes(tk) >= 12 ? 12 : 8;
   REQUIRE(fixed + (size_t)nstage * mk_stage_bytes(tk) <= SMEM_BUDGET, "activation width %zu too large for an 8-stage ring", kmax);
-  mega_fn fn = pick_mega(tk, c.head_dim, R, nstage, c.dtype);
+  mega_fn fn = pick_mega(tk, c.head_dim, R, nstage, c.dtype, c.n_experts > 0);
   REQUIRE(fn != nullptr, "no megakernel instantiation for tk=%d head_dim=%d gqa=%d stages=%d", tk, c.head_dim, R, nstage);
   const size_t smem = (size_t)nstage * mk_stage_bytes(tk) + fixed - 2048;
   e->mega_nstage = nstage;
@@ -257,6 +268,10 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.nreq = e->nreq; a.nslots = e->nreq + 1; a.req0 = e->cur_req; a.kv_req_stride = e->kv_req_stride;
   a.src_tokens = e->stage_tokens; a.src_hidden = e->stage_in; a.out_hidden = e->stage_out;
   a.xbuf_bytes = e->mega_xbuf;
+  a.E = c.n_experts; a.topk = c.experts_per_tok;
+  a.gu_stride = (size_t)2 * c.ffn * c.dim; a.dn_stride = (size_t)c.dim * c.ffn;
+  a.layer_tab_bytes = c.n_layers * (int)sizeof(LayerDev);
+  a.route_log = e->route_log;
   a.dbg = (mode == 0 && e->dbg_step >= 0) ? e->dbg : nullptr; a.dbg_step = e->dbg_step; a.dbg_cta = e->dbg_cta;
   CK(cudaMemsetAsync(e->bar_counter, 0, 4, st));
   void* params[] = {&a};
@@ -568,6 +583,7 @@ static void free_shard(xotb200_engine* e) {
   if (e->d_layers) { cudaFree(e->d_layers); e->d_layers = nullptr; }
   if (e->blob) { cudaFree(e->blob); e->blob = nullptr; }
   if (e->kv) { cudaFree(e->kv); e->kv = nullptr; }
+  if (e->route_log) { cudaFree(e->route_log); e->route_log = nullptr; }
   e->layers.clear();
   e->slots.clear();
   e->mega = nullptr;
@@ -618,6 +634,8 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   REQUIRE(cfg->dim % 512 == 0 && cfg->ffn % 512 == 0 && (cfg->n_heads * cfg->head_dim) % 512 == 0,
           "dim, ffn and n_heads*head_dim must be multiples of 512");
   REQUIRE(cfg->vocab % 2 == 0, "vocab must be even (row pairs)");
+  REQUIRE(cfg->n_experts == 0 || (cfg->n_experts >= 2 && cfg->n_experts <= NCW && cfg->experts_per_tok == 2),
+          "sparse MoE: 2..%d experts with 2 experts per token are implemented (got %d / %d)", NCW, cfg->n_experts, cfg->experts_per_tok);
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
@@ -637,7 +655,7 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   CK(cudaMalloc(&e->x, (size_t)D * 2));
   CK(cudaMalloc(&e->q, (size_t)Hq * hd * 2));
   CK(cudaMalloc(&e->attn_out, (size_t)Hq * hd * 2));
-  CK(cudaMalloc(&e->act, (size_t)cfg->ffn * 2));
+  CK(cudaMalloc(&e->act, (size_t)cfg->ffn * 2 * (cfg->n_experts > 0 ? 2 : 1)));   // MoE: both selected experts' activations
   CK(cudaMalloc(&e->logits, (size_t)cfg->vocab * 4));
   CK(cudaMalloc(&e->part_ml, (size_t)Hq * e->nsplit * 2 * 4));
   CK(cudaMalloc(&e->part_acc, (size_t)Hq * e->nsplit * hd * 4));
@@ -698,7 +716,9 @@ int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer) {
   const size_t A = 256;
   const size_t sz_norm = align_up(D * 2, A), sz_qkv = align_up((Hq + 2 * Hkv) * hd * D * 2, A),
                sz_o = align_up(D * Hq * hd * 2, A), sz_gu = align_up(2 * F * D * 2, A), sz_dn = align_up(D * F * 2, A);
-  const size_t per_layer = 2 * sz_norm + sz_qkv + sz_o + sz_gu + sz_dn;
+  const size_t E = c.n_experts, nexp = E ? E : 1;
+  const size_t sz_router = E ? align_up(E * D * 2, A) : 0;
+  const size_t per_layer = 2 * sz_norm + sz_qkv + sz_o + nexp * (sz_gu + sz_dn) + sz_router;
   const size_t sz_emb = align_up(V * D * 2, A);
   const bool own_head = e->last;   // the head is streamed in K-panel layout, the embedding is gathered row-wise: a tied
                                    // model keeps both copies when one shard holds both
@@ -716,7 +736,8 @@ int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer) {
   for (size_t li = 0; li < nl; ++li) {
     LayerW& w = e->layers[li];
     w.attn_norm = take(sz_norm); w.wqkv = take(sz_qkv); w.wo = take(sz_o);
-    w.mlp_norm = take(sz_norm); w.wgu = take(sz_gu); w.wdown = take(sz_dn);
+    w.mlp_norm = take(sz_norm); w.wgu = take(nexp * sz_gu); w.wdown = take(nexp * sz_dn);
+    w.router = E ? take(sz_router) : nullptr;
     const int l = start_layer + (int)li;
     const std::string pre = "model.layers." + std::to_string(l) + ".";
     const int t = l * 16;
@@ -730,9 +751,23 @@ int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer) {
     add("self_attn.v_proj.weight", w.wqkv, (int)(Hkv * hd), (int)D, 0, 1, (int)((Hq + Hkv) * hd), 3, 0.f, nqkv, tk);
     add("self_attn.o_proj.weight", w.wo, (int)D, (int)(Hq * hd), 0, 1, 0, 4, 0.f, (int)D, tk);
     add("post_attention_layernorm.weight", w.mlp_norm, 1, (int)D, 0, 1, 0, 5, 1.0f, 1, 0);
-    add("mlp.gate_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 0, 6, 0.f, (int)(2 * F), tk);
-    add("mlp.up_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 1, 7, 0.f, (int)(2 * F), tk);
-    add("mlp.down_proj.weight", w.wdown, (int)D, (int)F, 0, 1, 0, 8, 0.f, (int)D, tk);
+    if (E) {
+      // on-disk Mixtral names (w1 = gate, w3 = up, w2 = down); tensor ids as in synth.py: G_MOE + layer*64 + ...
+      const int tm = (1 << 21) + l * 64 - t;
+      add("block_sparse_moe.gate.weight", w.router, (int)E, (int)D, 0, 1, 0, tm, 0.f, (int)E, 0);
+      for (int x = 0; x < (int)E; ++x) {
+        const std::string ex = "block_sparse_moe.experts." + std::to_string(x) + ".";
+        bf16* gu = w.wgu + (size_t)x * (sz_gu / 2);
+        bf16* dn = w.wdown + (size_t)x * (sz_dn / 2);
+        add((ex + "w1.weight").c_str(), gu, (int)F, (int)D, 0, 2, 0, tm + 1 + 3 * x, 0.f, (int)(2 * F), tk);
+        add((ex + "w3.weight").c_str(), gu, (int)F, (int)D, 0, 2, 1, tm + 2 + 3 * x, 0.f, (int)(2 * F), tk);
+        add((ex + "w2.weight").c_str(), dn, (int)D, (int)F, 0, 1, 0, tm + 3 + 3 * x, 0.f, (int)D, tk);
+      }
+    } else {
+      add("mlp.gate_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 0, 6, 0.f, (int)(2 * F), tk);
+      add("mlp.up_proj.weight", w.wgu, (int)F, (int)D, 0, 2, 1, 7, 0.f, (int)(2 * F), tk);
+      add("mlp.down_proj.weight", w.wdown, (int)D, (int)F, 0, 1, 0, 8, 0.f, (int)D, tk);
+    }
   }
   if (e->first)
     e->slots.insert({"model.embed_tokens.weight", TensorSlot{e->embed, (int)V, (int)D, 0, 1, 0, (1 << 20), 0.02f, 0.f, false, (int)V, 0}});
@@ -852,7 +887,12 @@ int xotb200_begin_batch(xotb200_engine* e, int max_total_len, int n_requests) {
     e->nreq = n_requests;
     e->kv_req_stride = nl * 2 * (size_t)c.n_kv_heads * e->L * c.head_dim;
     CK(cudaMalloc(&e->kv, (size_t)e->nreq * e->kv_req_stride * 2));
+    if (c.n_experts > 0) {
+      if (e->route_log) { CK(cudaFree(e->route_log)); e->route_log = nullptr; }
+      CK(cudaMalloc(&e->route_log, (size_t)e->L * nl * 4));
+    }
   }
+  if (e->route_log) CK(cudaMemsetAsync(e->route_log, 0xff, (size_t)e->L * nl * 4, e->stream));
   if (max_total_len > e->rope_len) {
     // RoPE table: theta_j in fp32, angle = fp32(pos * theta_j), cos/sin correctly rounded
     const int half = c.head_dim / 2;
@@ -890,7 +930,7 @@ int xotb200_begin_batch(xotb200_engine* e, int max_total_len, int n_requests) {
     std::vector<LayerDev> h(nl);
     for (size_t li = 0; li < nl; ++li) {
       const LayerW& w = e->layers[li];
-      h[li] = LayerDev{w.attn_norm, w.wqkv, w.wo, w.mlp_norm, w.wgu, w.wdown,
+      h[li] = LayerDev{w.attn_norm, w.wqkv, w.wo, w.mlp_norm, w.wgu, w.wdown, w.router,
                        e->kv + (li * 2 + 0) * (size_t)c.n_kv_heads * e->L * c.head_dim,
                        e->kv + (li * 2 + 1) * (size_t)c.n_kv_heads * e->L * c.head_dim};
     }
@@ -954,7 +994,9 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
     CK(cudaGetLastError());
     e->launches++;
   }
-  const bool use_tc = e->prefill_mode == 2 || (e->prefill_mode == 0 && n_tokens >= 8);
+  REQUIRE(!(e->prefill_mode == 2 && e->cfg.n_experts > 0), "tensor-core prefill is not implemented for sparse-MoE shards (use mode 0 or 1)");
+  // sparse-MoE shards prefill position by position through the decode kernel (expert choice differs per position)
+  const bool use_tc = e->cfg.n_experts == 0 && (e->prefill_mode == 2 || (e->prefill_mode == 0 && n_tokens >= 8));
   if (use_tc) {
     if (int rc = prefill_tc(e, n_tokens, pos0, st)) return rc;     // GEMM-shaped: 5th-gen tensor cores
   } else {
@@ -1133,6 +1175,16 @@ int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16
   return 0;
 }
 
+int xotb200_debug_routing(xotb200_engine* e, int32_t* out, int n_positions) {
+  REQUIRE(e && out && e->start >= 0, "bad argument");
+  REQUIRE(e->cfg.n_experts > 0 && e->route_log, "not a sparse-MoE shard with an open request");
+  REQUIRE(n_positions >= 1 && n_positions <= e->L, "n_positions %d out of range (KV capacity %d)", n_positions, e->L);
+  CK(cudaSetDevice(e->device));
+  const size_t nl = e->end - e->start + 1;
+  MEMCPY_SYNC(e, out, e->route_log, (size_t)n_positions * nl * 4, cudaMemcpyDeviceToHost);
+  return 0;
+}
+
 int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, int n_u64) {
   REQUIRE(e, "null engine");
   CK(cudaSetDevice(e->device));
@@ -1165,7 +1217,8 @@ int xotb200_step_bytes(xotb200_engine* e, int ctx, int64_t* bytes) {
   const xotb200_model_cfg& c = e->cfg;
   const int64_t D = c.dim, F = c.ffn, Hq = c.n_heads, Hkv = c.n_kv_heads, hd = c.head_dim, V = c.vocab;
   const int64_t nl = e->end - e->start + 1;
-  int64_t b = nl * 2 * (D * Hq * hd + 2 * D * Hkv * hd + Hq * hd * D + 3 * D * F + 2 * D);
+  const int64_t mlp = c.n_experts > 0 ? (int64_t)c.n_experts * D + (int64_t)c.experts_per_tok * 3 * D * F : 3 * D * F;   // active experts only
+  int64_t b = nl * 2 * (D * Hq * hd + 2 * D * Hkv * hd + Hq * hd * D + mlp + 2 * D);
   if (e->last) b += 2 * (V * D + D);
   if (e->first) b += 2 * D;
   b += 2 * 2 * Hkv * hd * nl * (int64_t)ctx + 2 * 2 * Hkv * hd * nl;

@@ -44,7 +44,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 struct LayerDev {
-  const bf16 *attn_norm, *wqkv, *wo, *mlp_norm, *wgu, *wdown;
+  const bf16 *attn_norm, *wqkv, *wo, *mlp_norm, *wgu, *wdown;   // MoE: wgu / wdown = expert 0, expert e at + e * stride
+  const bf16* router;        // MoE: [E, D] row-major (NULL for a dense MLP)
   bf16 *k_cache, *v_cache;   // [Hkv, L, hd] each
 };
 
@@ -76,6 +77,13 @@ struct MegaArgs {
   const int* src_tokens;     // direct, first shard: [n_steps]
   const bf16* src_hidden;    // direct, other shards: [n_steps, D]
   bf16* out_hidden;          // direct, non-last shard: [n_steps, D]
+  // Mixtral-style sparse MoE MLP (E == 0: dense).  Every CTA evaluates the router redundantly from the normalised x it
+  // already holds in shared memory (E rows of D: no extra grid barrier), the gate/up and down ops then run as TWO
+  // segments (the selected experts in ascending index) over the same row partition.
+  int E, topk;
+  size_t gu_stride, dn_stride;   // elements between consecutive experts' gate/up and down matrices
+  int layer_tab_bytes;           // size of the shared-memory layer table (the MoE stash follows it)
+  int* route_log;                // [L][nl] experts chosen for request 0 at (position, local layer): lo | hi << 8 (parity tests)
   int xbuf_bytes;            // shared-memory activation buffer size
   unsigned long long* dbg;   // optional timeline [n_ops+1][4] of CTA dbg_cta for step dbg_step (NULL = off)
   int dbg_step, dbg_cta;

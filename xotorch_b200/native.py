@@ -38,6 +38,8 @@ def cfg_from_hf(hf: dict) -> ModelCfg:
   c.norm_eps = float(hf["rms_norm_eps"])
   c.tie_embeddings = 1 if hf.get("tie_word_embeddings", False) else 0
   c.dtype = dtype
+  c.n_experts = int(hf.get("num_local_experts") or 0)          # Mixtral-style sparse MoE MLP
+  c.experts_per_tok = int(hf.get("num_experts_per_tok") or 0)
   if rs is not None:
     c.rope_kind = _lib.ROPE_LLAMA3
     c.rope_factor = float(rs.get("factor", 32))
@@ -184,6 +186,14 @@ class NativeShard:
     check(self.lib.xotb200_debug_gemm(self.h, a.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), S, N, K, int(tk),
                                       out.ctypes.data_as(C.c_void_p)))
     return out
+
+  def debug_routing(self, n_positions: int) -> np.ndarray:
+    """[n_positions, local layers, 2] experts chosen by the router (ascending index) for request 0; -1 = not run"""
+    nl = self.end - self.start + 1
+    out = np.empty(n_positions * nl, dtype=np.int32)
+    check(self.lib.xotb200_debug_routing(self.h, out.ctypes.data_as(C.POINTER(C.c_int32)), int(n_positions)))
+    out = out.reshape(n_positions, nl)
+    return np.stack([np.where(out < 0, -1, out & 0xff), np.where(out < 0, -1, (out >> 8) & 0xff)], axis=-1)
 
   def debug_timeline(self, step: int, cta: int = 0, read: bool = False):
     n = (4 * self.cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8

@@ -24,6 +24,8 @@ import torch
 # tensor "kinds" inside one decoder layer; tensor_id = layer*16 + kind
 K_ATTN_NORM, K_Q, K_K, K_V, K_O, K_MLP_NORM, K_GATE, K_UP, K_DOWN = range(9)
 G_EMBED, G_NORM, G_HEAD = (1 << 20), (1 << 20) + 1, (1 << 20) + 2
+# mixture-of-experts tensors of a layer: tensor_id = G_MOE + layer*64 + {0: router, 1 + 3*e + {0: w1 gate, 1: w3 up, 2: w2 down}}
+G_MOE = 1 << 21
 
 _M64 = (1 << 64) - 1
 _C_SEED = 0x9E3779B97F4A7C15
@@ -85,6 +87,8 @@ class ModelShape:
   tie: bool = False      # tie_word_embeddings
   rope_scaling: Optional[dict] = None
   dtype: str = "bfloat16"
+  n_experts: int = 0     # num_local_experts (0 = dense SwiGLU MLP)
+  top_k: int = 0         # num_experts_per_tok
 
 
 _LLAMA32_SCALING = {"factor": 32.0, "high_freq_factor": 4.0, "low_freq_factor": 1.0,
@@ -103,12 +107,28 @@ PRESETS: Dict[str, ModelShape] = {
                              rope_scaling=dict(_LLAMA32_SCALING)),
   "llama-3-8b": ModelShape("llama-3-8b", 32, 4096, 14336, 32, 8, 128, 128256),
   "llama-3-70b": ModelShape("llama-3-70b", 80, 8192, 28672, 64, 8, 128, 128256, dtype="float16"),
+  # Mixtral-style sparse MoE MLP: router + top-2 of 8 SwiGLU experts
+  "tiny-mixtral": ModelShape("tiny-mixtral", 4, 512, 1024, 8, 2, 64, 2048, rope_theta=1e6, max_pos=2048, n_experts=8, top_k=2),
+  "tiny-mixtral-hd128": ModelShape("tiny-mixtral-hd128", 3, 1024, 2048, 8, 2, 128, 4096, rope_theta=1e6, max_pos=2048,
+                                   n_experts=4, top_k=2),
+  "mixtral-8x7b": ModelShape("mixtral-8x7b", 32, 4096, 14336, 32, 8, 128, 32000, rope_theta=1e6, max_pos=32768,
+                             n_experts=8, top_k=2),
   # same dimensions with bf16 weights: what the engine runs today (fp16 weights are not implemented yet)
   "llama-3-70b-bf16": ModelShape("llama-3-70b-bf16", 80, 8192, 28672, 64, 8, 128, 128256),
 }
 
 
 def hf_config(shape: ModelShape) -> dict:
+  if shape.n_experts:
+    return {
+      "architectures": ["MixtralForCausalLM"], "model_type": "mixtral", "hidden_act": "silu",
+      "hidden_size": shape.dim, "intermediate_size": shape.ffn, "num_hidden_layers": shape.n_layers,
+      "num_attention_heads": shape.n_heads, "num_key_value_heads": shape.n_kv_heads, "head_dim": shape.head_dim,
+      "vocab_size": shape.vocab, "rms_norm_eps": shape.norm_eps, "rope_theta": shape.rope_theta, "rope_scaling": None,
+      "max_position_embeddings": shape.max_pos, "tie_word_embeddings": False, "torch_dtype": shape.dtype,
+      "attention_dropout": 0.0, "bos_token_id": 1, "eos_token_id": 2, "sliding_window": None,
+      "num_local_experts": shape.n_experts, "num_experts_per_tok": shape.top_k, "router_jitter_noise": 0.0,
+    }
   return {
     "architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_act": "silu",
     "hidden_size": shape.dim, "intermediate_size": shape.ffn, "num_hidden_layers": shape.n_layers,
@@ -127,7 +147,8 @@ def shape_from_hf_config(cfg: dict, name: str = "model") -> ModelShape:
     head_dim=cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"], vocab=cfg["vocab_size"],
     rope_theta=float(cfg.get("rope_theta", 10000.0)), norm_eps=float(cfg["rms_norm_eps"]),
     max_pos=int(cfg["max_position_embeddings"]), tie=bool(cfg.get("tie_word_embeddings", False)),
-    rope_scaling=cfg.get("rope_scaling"), dtype=str(cfg.get("torch_dtype", "bfloat16")))
+    rope_scaling=cfg.get("rope_scaling"), dtype=str(cfg.get("torch_dtype", "bfloat16")),
+    n_experts=int(cfg.get("num_local_experts") or 0), top_k=int(cfg.get("num_experts_per_tok") or 0))
 
 
 W_STD = 0.02  # weights ~ N(0, 0.02^2), norm scales = 1 + N(0, 0.02^2)
@@ -149,10 +170,22 @@ def hf_tensor_specs(shape: ModelShape, layers: Optional[Iterable[int]] = None,
       (p + "self_attn.v_proj.weight", t + K_V, (Hkv * hd, D), W_STD, 0.0),
       (p + "self_attn.o_proj.weight", t + K_O, (D, Hq * hd), W_STD, 0.0),
       (p + "post_attention_layernorm.weight", t + K_MLP_NORM, (D,), W_STD, 1.0),
-      (p + "mlp.gate_proj.weight", t + K_GATE, (F, D), W_STD, 0.0),
-      (p + "mlp.up_proj.weight", t + K_UP, (F, D), W_STD, 0.0),
-      (p + "mlp.down_proj.weight", t + K_DOWN, (D, F), W_STD, 0.0),
     ]
+    if shape.n_experts:   # on-disk names of the Mixtral checkpoints (w1 = gate, w3 = up, w2 = down)
+      m, tm = p + "block_sparse_moe.", G_MOE + l * 64
+      specs.append((m + "gate.weight", tm, (shape.n_experts, D), W_STD, 0.0))
+      for e in range(shape.n_experts):
+        specs += [
+          (m + f"experts.{e}.w1.weight", tm + 1 + 3 * e, (F, D), W_STD, 0.0),
+          (m + f"experts.{e}.w3.weight", tm + 2 + 3 * e, (F, D), W_STD, 0.0),
+          (m + f"experts.{e}.w2.weight", tm + 3 + 3 * e, (D, F), W_STD, 0.0),
+        ]
+    else:
+      specs += [
+        (p + "mlp.gate_proj.weight", t + K_GATE, (F, D), W_STD, 0.0),
+        (p + "mlp.up_proj.weight", t + K_UP, (F, D), W_STD, 0.0),
+        (p + "mlp.down_proj.weight", t + K_DOWN, (D, F), W_STD, 0.0),
+      ]
   if with_head:
     specs.append(("model.norm.weight", G_NORM, (D,), W_STD, 1.0))
     if not shape.tie:
