@@ -181,7 +181,7 @@ def run_reference(args):
     vals.append(v)
   v = float(np.mean(vals))
   line = {
-    "impl": "reference", "metric": "Llama-3-8B greedy decode tokens/sec (128-prompt/512-gen, batch 1)", "value": round(v, 4),
+    "impl": "reference", "metric": ("Llama-3-8B" if MODEL == "llama-3-8b" else MODEL) + f" greedy decode tokens/sec ({N_PROMPT}-prompt/{N_GEN}-gen, batch 1)", "value": round(v, 4),
     "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
     "ms_per_step": round(N_GEN / v * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
     "dtype": "bf16", "data": "synthetic",
@@ -363,13 +363,13 @@ def run_b200(args):
       hop = {"p50_us": round(float(np.median(hs)), 2), "p90_us": round(float(np.percentile(hs, 90)), 2),
              "how": "per ring turn: (rank-0 ring period - sum over shards of [flag observed -> result posted], each on its own globaltimer) / n_hops"}
     line = {
-      "metric": "Llama-3-8B greedy decode tokens/sec (128-prompt/512-gen, batch 1)", "value": round(value, 2), "unit": "tokens/s",
-      "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 3),
-      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-      "config": {"workload": f"{MODEL} shape, synthetic bf16 weights (seed {SEED}, device-generated), {N_PROMPT}-token prompt / "
+      "metric": ("Llama-3-8B" if MODEL == "llama-3-8b" else MODEL) + f" greedy decode tokens/sec ({N_PROMPT}-prompt/{N_GEN}-gen, batch 1)",
+      "value": round(value, 2), "unit": "tokens/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 3),
+      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16" if shape.dtype == "float16" else "bf16", "data": "synthetic",
+      "config": {"workload": f"{MODEL} shape, synthetic {shape.dtype} weights (seed {SEED}, device-generated), {N_PROMPT}-token prompt / "
                              f"{N_GEN} generated, batch 1, greedy; step = one request, decode phase timed",
                  "shards": n, "layers_per_shard": (b - a + 1), "partitioning": "ring, equal HBM",
-                 "l2_policy": "inputs larger than L2 (15 GB of weights streamed per token vs 126 MB L2)",
+                 "l2_policy": f"inputs larger than L2 ({step_bytes_total / 1e9:.1f} GB of weights + KV streamed per token vs 126 MB L2)",
                  "prefill_ms_host_api": round(prefill_ms, 1), "first_ids": first_ids,
                  "ring_ids_equal_api_ids": ids_match_api},
       "clocks": clocks, "gpu_launches": int(gpu_launches),
@@ -395,7 +395,14 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  # the other BASELINE.json configs through the same contract (defaults = the headline config):
+  #   --model llama-3-70b --gpus 8 --prompt 4096      (fp16, must shard to fit)     --model mixtral-8x7b --gpus 4
+  from xotorch_b200.synth import PRESETS
+  ap.add_argument("--model", default=MODEL, choices=sorted(k for k in PRESETS if not k.startswith("tiny")))
+  ap.add_argument("--prompt", type=int, default=N_PROMPT)
+  ap.add_argument("--gen", type=int, default=N_GEN)
   args = ap.parse_args()
+  globals().update(MODEL=args.model, N_PROMPT=args.prompt, N_GEN=args.gen)
   if args.impl == "reference":
     run_reference(args)
   else:

@@ -24,12 +24,25 @@ GOLD = ROOT / "tests" / "golden"
 from oracle.ref_engine import RefEngine, RefShard, model_config_from_hf, generate_ids  # noqa: E402
 from xotorch_b200.synth import PRESETS, hf_config, synth_state_dict, synth_prompt  # noqa: E402
 
-TINY = ["tiny-llama-hd64", "tiny-llama-hd128", "tiny-llama-3.2"]
+TINY = ["tiny-llama-hd64", "tiny-llama-hd128", "tiny-llama-3.2", "tiny-mixtral"]
 
 
 def hf_logits(shape, sd, prompt, dtype):
   from transformers import LlamaConfig, LlamaForCausalLM
   hc = {k: v for k, v in hf_config(shape).items() if k not in ("architectures", "model_type", "torch_dtype")}
+  if shape.n_experts:   # the reference has no MoE path: the oracle's MoE block restates HF Mixtral (fused 3-D expert params)
+    from transformers import MixtralConfig, MixtralForCausalLM
+    m = MixtralForCausalLM(MixtralConfig(**hc)).to(dtype).eval()
+    conv = {k: v.to(dtype) for k, v in sd.items() if "block_sparse_moe" not in k}
+    for l in range(shape.n_layers):
+      p = f"model.layers.{l}."
+      ex = lambda e, w: sd[p + f"block_sparse_moe.experts.{e}.{w}.weight"]
+      conv[p + "mlp.gate.weight"] = sd[p + "block_sparse_moe.gate.weight"].to(dtype)
+      conv[p + "mlp.experts.gate_up_proj"] = torch.stack([torch.cat([ex(e, "w1"), ex(e, "w3")], 0) for e in range(shape.n_experts)]).to(dtype)
+      conv[p + "mlp.experts.down_proj"] = torch.stack([ex(e, "w2") for e in range(shape.n_experts)]).to(dtype)
+    m.load_state_dict(conv, strict=True)
+    with torch.no_grad():
+      return m(torch.tensor(prompt).long()).logits[0].float().numpy()
   m = LlamaForCausalLM(LlamaConfig(**hc)).to(dtype).eval()
   m.load_state_dict({k: v.to(dtype) for k, v in sd.items()}, strict=not shape.tie)
   with torch.no_grad():

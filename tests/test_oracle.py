@@ -12,7 +12,7 @@ from oracle.ref_engine import (RefEngine, RefShard, model_config_from_hf, genera
 from xotorch_b200.synth import PRESETS, hf_config, synth_state_dict, synth_prompt
 
 GOLD = Path(__file__).resolve().parent / "golden"
-TINY = ["tiny-llama-hd64", "tiny-llama-hd128", "tiny-llama-3.2"]
+TINY = ["tiny-llama-hd64", "tiny-llama-hd128", "tiny-llama-3.2", "tiny-mixtral"]
 
 
 def _engine(name, a, b, dtype=None):
@@ -54,6 +54,57 @@ def test_oracle_vs_hf_live_fp32():
     hf = m(torch.tensor(prompt).long()).logits[0, -1].numpy()
   _, logits, _ = generate_ids([_engine(name, 0, shape.n_layers - 1, dtype=torch.float32)], prompt, 1)
   assert np.abs(logits[0] - hf).max() < 2e-5
+
+
+def test_oracle_moe_vs_hf_mixtral_live():
+  """The sparse-MoE block of the oracle restates HF transformers' Mixtral (the reference has no MoE path): same synthetic
+  weights through MixtralForCausalLM (fused 3-D expert parameters, half-split RoPE) must give the same logits — fp32 to
+  rounding noise, bf16 to a few ulps (no routing near-tie at this position: checked through the route log)."""
+  from transformers import MixtralConfig, MixtralForCausalLM
+  name = "tiny-mixtral"
+  shape = PRESETS[name]
+  sd = synth_state_dict(shape, 1234)
+  prompt = synth_prompt(shape.vocab, 12)
+  hc = {k: v for k, v in hf_config(shape).items() if k not in ("architectures", "model_type", "torch_dtype")}
+
+  def hf_logits(dtype):
+    m = MixtralForCausalLM(MixtralConfig(**hc)).to(dtype).eval()
+    conv = {k: v.to(dtype) for k, v in sd.items() if "block_sparse_moe" not in k}
+    for l in range(shape.n_layers):
+      p = f"model.layers.{l}."
+      ex = lambda e, w: sd[p + f"block_sparse_moe.experts.{e}.{w}.weight"]
+      conv[p + "mlp.gate.weight"] = sd[p + "block_sparse_moe.gate.weight"].to(dtype)
+      conv[p + "mlp.experts.gate_up_proj"] = torch.stack([torch.cat([ex(e, "w1"), ex(e, "w3")], 0) for e in range(shape.n_experts)]).to(dtype)
+      conv[p + "mlp.experts.down_proj"] = torch.stack([ex(e, "w2") for e in range(shape.n_experts)]).to(dtype)
+    m.load_state_dict(conv, strict=True)
+    with torch.no_grad():
+      return m(torch.tensor(prompt).long()).logits[0, -1].float().numpy()
+
+  e32 = _engine(name, 0, shape.n_layers - 1, dtype=torch.float32)
+  _, l32, _ = generate_ids([e32], prompt, 1)
+  assert np.abs(l32[0] - hf_logits(torch.float32)).max() < 2e-5
+  eb = _engine(name, 0, shape.n_layers - 1)
+  eb.model.route_log = []
+  _, lb, _ = generate_ids([eb], prompt, 1)
+  assert len(eb.model.route_log) == shape.n_layers * 12
+  assert np.abs(lb[0] - hf_logits(torch.bfloat16)).max() < 0.05
+
+
+def test_oracle_moe_forced_routing_and_log():
+  """Imposing the oracle's own choices changes nothing; imposing another pair is applied and reported with its distance."""
+  name = "tiny-mixtral"
+  prompt = synth_prompt(PRESETS[name].vocab, 8)
+  a = _engine(name, 0, 3); a.model.route_log = []
+  _, la, _ = generate_ids([a], prompt, 3)
+  own = {(r[0], r[1]): r[2] for r in a.model.route_log}
+  b = _engine(name, 0, 3); b.model.forced_routes = dict(own); b.model.route_log = []
+  _, lb, _ = generate_ids([b], prompt, 3)
+  assert np.array_equal(la, lb) and all(r[2] == r[3] and r[4] < 1e-6 for r in b.model.route_log)
+  other = tuple(sorted({0, 1, 2} - set(own[(1, 5)]))[:2])
+  c = _engine(name, 0, 3); c.model.forced_routes = {**own, (1, 5): other}; c.model.route_log = []
+  _, lc, _ = generate_ids([c], prompt, 3)
+  dis = [r for r in c.model.route_log if r[2] != r[3]]
+  assert len(dis) >= 1 and dis[0][:2] == (1, 5) and dis[0][3] == other and dis[0][4] > 0 and not np.array_equal(la, lc)
 
 
 @pytest.mark.parametrize("split", [[(0, 1), (2, 3)], [(0, 0), (1, 2), (3, 3)], [(0, 0), (1, 1), (2, 2), (3, 3)]])
