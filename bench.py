@@ -314,7 +314,7 @@ def run_b200(args):
   #      Reported beside the headline, never instead of it: `value` stays the single-request metric BASELINE.json names. ----
   pipelined = None
   if n > 1:
-    Bq, gen_q = min(n, 8), 256
+    Bq, gen_q = min(n, 8), min(256, N_GEN)
     prompts_q = np.concatenate([synth_prompt(V, N_PROMPT, seed=SEED + 1 + r) for r in range(Bq)])
     ring.generate_batch(prompts_q, gen_q)                  # warm
     barrier()
