@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from xotorch_b200.synth import PRESETS, hf_config, synth_prompt
-from tests.test_gpu_parity import _oracle, _native, _api_generate, ATOL, RTOL
+from tests.test_gpu_parity import _oracle, _native, _api_generate, _oracle_with_routing, ATOL, RTOL
 
 
 def _bf16_bits(x: torch.Tensor) -> np.ndarray:
@@ -85,3 +85,23 @@ def test_tc_prefill_real_dims_vs_oracle():
   ids, logits = _api_generate([e], prompt, 3, force_ids=o_ids)
   err = np.abs(logits - o_logits); std = float(o_logits.std())
   assert float(np.sqrt((err ** 2).mean())) <= 0.02 * std and err.max() <= 0.10 * std, (err.max(), std)
+
+
+@pytest.mark.parametrize("shape_name,n_prompt", [("tiny-mixtral", 40), ("tiny-mixtral", 300), ("tiny-mixtral-hd128", 140)])
+def test_tc_prefill_sparse_moe_matches_oracle(shape_name, n_prompt):
+  """Sparse-MoE prompt on the tensor cores (router -> per-expert row blocks -> tcgen05 GEMMs per expert -> combine) and
+  through the decode kernel: each against the oracle re-run with that path's expert choices (near-ties asserted)."""
+  from xotorch_b200.synth import synth_state_dict
+  shape = PRESETS[shape_name]
+  full = [(0, shape.n_layers - 1)]
+  n_gen = 4
+  prompt, (o_ids, _, _) = _oracle(shape_name, full, n_prompt, n_gen)
+  sd = synth_state_dict(shape, 1234)
+  for mode in (2, 1):
+    eng = _native(shape_name, full)
+    eng[0].set_prefill_mode(mode)
+    ids, logits = _api_generate(eng, prompt, n_gen, force_ids=o_ids)
+    o_logits, gaps = _oracle_with_routing(shape, sd, prompt, n_gen, o_ids, eng[0].debug_routing(n_prompt + n_gen - 1))
+    err = np.abs(logits - o_logits)
+    assert (err <= ATOL + RTOL * np.abs(o_logits)).all(), f"mode {mode}: max err {err.max():.4f}"
+

@@ -15,7 +15,7 @@ shape = PRESETS[name]
 e = NativeShard(hf_config(shape), 0)
 e.set_shard(0, shape.n_layers - 1)
 e.init_synthetic(1234)
-params = 2 * (e.weight_bytes() / 2)            # flop per token ~ 2 * parameters touched
+params = e.step_bytes(0)                       # flop per token ~ 2 * parameters touched = bytes touched per token (16-bit weights)
 for n in lens:
   prompt = synth_prompt(shape.vocab, n)
   best = 1e9

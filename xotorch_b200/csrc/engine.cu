@@ -153,6 +153,12 @@ struct xotb200_engine {
   CUtensorMap tm_xn, tm_ao, tm_act;
   std::map<int, std::vector<CUtensorMap>> tm_w;   // per N-tile width: 4 per local layer (qkv, o, gu, down) + head
   int tc_cap = 0;                  // token rows the tensor-core scratch buffers currently hold
+  // sparse MoE prefill: gathered per-expert row blocks (rows_max = 2 * tc_cap + E * 128) and the device-side plan
+  bf16 *moe_xg = nullptr, *moe_gu = nullptr, *moe_act = nullptr, *moe_y = nullptr;
+  int *moe_route_e = nullptr, *moe_row_of = nullptr, *moe_row_token = nullptr, *moe_exp_info = nullptr;
+  float* moe_route_w = nullptr;
+  int moe_rows = 0;
+  CUtensorMap tm_moe_xg, tm_moe_act;
   unsigned long long* dbg = nullptr;
   int dbg_step = -1, dbg_cta = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -358,7 +364,7 @@ static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CU
     CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT, NS)));
     attr_done[key] = true;
   }
-  const int mtiles = epi == TCE_HEAD_LAST ? 1 : (a.S + TC_M - 1) / TC_M - a.mt0;
+  const int mtiles = a.grid_m > 0 ? a.grid_m : (epi == TCE_HEAD_LAST ? 1 : (a.S + TC_M - 1) / TC_M - a.mt0);
   fn<<<dim3(mtiles, a.N / NT), TC_THREADS, tc_smem_bytes(NT, NS), st>>>(tmA, tmB, a);
   CK(cudaGetLastError());
   e->launches++;
@@ -391,6 +397,16 @@ static int ensure_tm_w(xotb200_engine* e, int nt) {
   }
   if (e->last)
     if (int rc = mk(&v[4 * nl], e->lm_head, c.vocab, D)) return rc;
+  if (c.n_experts > 0) {   // sparse MoE: per-expert gate/up and down maps follow at 4*nl + 1 + (li*E + x)*2 + {0, 1}
+    const int E = c.n_experts;
+    v.resize((size_t)4 * nl + 1 + (size_t)2 * nl * E, CUtensorMap{});
+    for (int li = 0; li < nl; ++li)
+      for (int x = 0; x < E; ++x) {
+        const LayerW& w = e->layers[li];
+        if (int rc = mk(&v[4 * nl + 1 + (li * E + x) * 2 + 0], w.wgu + (size_t)x * 2 * F * D, 2 * F, D)) return rc;
+        if (int rc = mk(&v[4 * nl + 1 + (li * E + x) * 2 + 1], w.wdown + (size_t)x * D * F, D, F)) return rc;
+      }
+  }
   e->tm_w[nt] = std::move(v);
   return 0;
 }
@@ -402,7 +418,8 @@ static int prepare_tc(xotb200_engine* e, int n_tokens) {
   if (need > e->tc_cap) {   // scratch for one chunk of `need` token rows (grown on demand, kept across requests)
     CK(cudaStreamSynchronize(e->stream));
     bf16** bufs[] = {&e->tc_x, &e->tc_xn, &e->tc_qkv, &e->tc_q, &e->tc_ao, &e->tc_gu, &e->tc_act};
-    const size_t cols[] = {D, D, nqkv, qd, qd, 2 * F, F};
+    const size_t fdense = c.n_experts > 0 ? 8 : F;   // sparse MoE shards use the gathered buffers below instead of tc_gu / tc_act
+    const size_t cols[] = {D, D, nqkv, qd, qd, 2 * fdense, fdense};
     for (int i = 0; i < 7; ++i) {
       if (*bufs[i]) CK(cudaFree(*bufs[i]));
       *bufs[i] = nullptr;
@@ -410,9 +427,26 @@ static int prepare_tc(xotb200_engine* e, int n_tokens) {
       MEMSET_SYNC(e, *bufs[i], 0, (size_t)need * cols[i] * 2);
     }
     e->tc_cap = need;
+    if (c.n_experts > 0) {
+      const size_t rows = (size_t)2 * need + (size_t)c.n_experts * TC_M;
+      void** mb[] = {(void**)&e->moe_xg, (void**)&e->moe_gu, (void**)&e->moe_act, (void**)&e->moe_y, (void**)&e->moe_route_e,
+                     (void**)&e->moe_route_w, (void**)&e->moe_row_of, (void**)&e->moe_row_token, (void**)&e->moe_exp_info};
+      const size_t mbytes[] = {rows * D * 2, rows * 2 * F * 2, rows * F * 2, rows * D * 2, (size_t)need * 2 * 4, (size_t)need * 2 * 4,
+                               (size_t)need * 2 * 4, rows * 4, (size_t)(2 * c.n_experts + 1) * 4};
+      for (int i = 0; i < 9; ++i) {
+        if (*mb[i]) CK(cudaFree(*mb[i]));
+        *mb[i] = nullptr;
+        CK(cudaMalloc(mb[i], mbytes[i]));
+        MEMSET_SYNC(e, *mb[i], 0, mbytes[i]);
+      }
+      e->moe_rows = (int)rows;
+      if (int rc = make_tmap_act(&e->tm_moe_xg, e->moe_xg, (int)D, (int)rows)) return rc;
+      if (int rc = make_tmap_act(&e->tm_moe_act, e->moe_act, (int)F, (int)rows)) return rc;
+    }
     if (int rc = make_tmap_act(&e->tm_xn, e->tc_xn, (int)D, need)) return rc;
     if (int rc = make_tmap_act(&e->tm_ao, e->tc_ao, (int)qd, need)) return rc;
-    if (int rc = make_tmap_act(&e->tm_act, e->tc_act, (int)F, need)) return rc;
+    if (c.n_experts == 0)
+      if (int rc = make_tmap_act(&e->tm_act, e->tc_act, (int)F, need)) return rc;
   }
   return 0;
 }
@@ -422,6 +456,15 @@ static int tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, int widx, const Tc
   const TcCfg c = tc_cfg(a.N, epi == TCE_HEAD_LAST ? 1 : a.S);
   if (int rc = ensure_tm_w(e, c.nt)) return rc;
   return launch_tc_gemm(e, tmA, e->tm_w[c.nt][widx], a, epi, c, st);
+}
+
+// one expert GEMM of a sparse-MoE prefill: rows [exp_info[2x], +128 * exp_info[2x+1]) of the gathered buffer, weight map `widx`;
+// a.S = rows of the gathered buffer (all of them valid to write), grid.x = the most tiles one expert can get
+static int tc_gemm_expert(xotb200_engine* e, const CUtensorMap& tmA, int widx, TcGemmArgs a, int max_tiles, int avg_rows, cudaStream_t st) {
+  const TcCfg c = tc_cfg(a.N, avg_rows);
+  if (int rc = ensure_tm_w(e, c.nt)) return rc;
+  a.grid_m = max_tiles;
+  return launch_tc_gemm(e, tmA, e->tm_w[c.nt][widx], a, TCE_STORE, c, st);
 }
 
 template <int HD>
@@ -476,9 +519,34 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
       if (int rc = tc_gemm(e, e->tm_ao, 4 * li + 1, o, TCE_RESID, st)) return rc;
       DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.mlp_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
+      if (c.n_experts > 0) {
+        // ---- sparse MoE MLP: router -> plan -> gather -> per-expert gate/up -> SwiGLU -> per-expert down -> combine ----
+        const int E = c.n_experts, rows = e->moe_rows, max_tiles = (S + TC_M - 1) / TC_M, avg_rows = std::max(1, 2 * S / E);
+        int* rlog = (e->route_log && e->cur_req == 0) ? e->route_log + (size_t)(pos0 + m0) * nl : nullptr;
+        DT_LAUNCH(e, (moe_router_kernel<<<S, 256, 0, st>>>(e->tc_xn, w.router, D, E, e->moe_route_e, e->moe_route_w, rlog, nl, li)));
+        CK(cudaGetLastError());
+        moe_plan_kernel<<<1, 1024, 0, st>>>(e->moe_route_e, S, E, rows, e->moe_row_of, e->moe_row_token, e->moe_exp_info);
+        CK(cudaGetLastError());
+        DT_LAUNCH(e, (moe_gather_kernel<<<rows, 128, 0, st>>>(e->tc_xn, e->moe_row_token, e->moe_exp_info, E, e->moe_xg, D)));
+        CK(cudaGetLastError());
+        for (int x = 0; x < E; ++x) {
+          TcGemmArgs u{rows, 2 * F, D, e->tk, e->moe_gu, nullptr, 2 * F, 0, e->moe_exp_info + 2 * x};
+          if (int rc = tc_gemm_expert(e, e->tm_moe_xg, 4 * nl + 1 + (li * E + x) * 2 + 0, u, max_tiles, avg_rows, st)) return rc;
+        }
+        DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(rows, (F + 2047) / 2048), 256, 0, st>>>(e->moe_gu, e->moe_act, F, e->moe_exp_info + 2 * E)));
+        CK(cudaGetLastError());
+        for (int x = 0; x < E; ++x) {
+          TcGemmArgs d{rows, D, F, e->tk, e->moe_y, nullptr, D, 0, e->moe_exp_info + 2 * x};
+          if (int rc = tc_gemm_expert(e, e->tm_moe_act, 4 * nl + 1 + (li * E + x) * 2 + 1, d, max_tiles, avg_rows, st)) return rc;
+        }
+        DT_LAUNCH(e, (moe_combine_kernel<<<S, 256, 0, st>>>(e->tc_x, e->moe_y, e->moe_row_of, e->moe_route_w, D)));
+        CK(cudaGetLastError());
+        e->launches += 8;
+        continue;
+      }
       TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F, 0};
       if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 2, u, TCE_STORE, st)) return rc;
-      DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F)));
+      DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F, nullptr)));
       CK(cudaGetLastError());
       TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D, 0};
       if (int rc = tc_gemm(e, e->tm_act, 4 * li + 3, d, TCE_RESID, st)) return rc;
@@ -684,7 +752,8 @@ int xotb200_destroy(xotb200_engine* e) {
   cudaDeviceSynchronize();
   free_shard(e);
   if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
-  void* tcp[] = {e->tc_x, e->tc_xn, e->tc_qkv, e->tc_q, e->tc_ao, e->tc_gu, e->tc_act};
+  void* tcp[] = {e->tc_x, e->tc_xn, e->tc_qkv, e->tc_q, e->tc_ao, e->tc_gu, e->tc_act, e->moe_xg, e->moe_gu, e->moe_act, e->moe_y,
+                 e->moe_route_e, e->moe_route_w, e->moe_row_of, e->moe_row_token, e->moe_exp_info};
   for (void* p : tcp)
     if (p) cudaFree(p);
   void* ptrs[] = {e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
@@ -994,9 +1063,7 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
     CK(cudaGetLastError());
     e->launches++;
   }
-  REQUIRE(!(e->prefill_mode == 2 && e->cfg.n_experts > 0), "tensor-core prefill is not implemented for sparse-MoE shards (use mode 0 or 1)");
-  // sparse-MoE shards prefill position by position through the decode kernel (expert choice differs per position)
-  const bool use_tc = e->cfg.n_experts == 0 && (e->prefill_mode == 2 || (e->prefill_mode == 0 && n_tokens >= 8));
+  const bool use_tc = e->prefill_mode == 2 || (e->prefill_mode == 0 && n_tokens >= 8);
   if (use_tc) {
     if (int rc = prefill_tc(e, n_tokens, pos0, st)) return rc;     // GEMM-shaped: 5th-gen tensor cores
   } else {

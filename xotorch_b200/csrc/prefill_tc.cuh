@@ -35,6 +35,8 @@ struct TcGemmArgs {
   float* logits;    // HEAD_LAST: [N] fp32, row S-1 only (bf16-valued)
   int ld;           // row stride of `out` in elements
   int mt0;          // first token tile of this launch (0, or the last tile for HEAD_LAST)
+  const int* tile_info;   // sparse MoE (NULL otherwise): {first row of this expert's block, its 128-row tiles}; CTAs beyond exit
+  int grid_m;             // sparse MoE: token tiles to launch (the most one expert can get); 0 = ceil(S / 128) - mt0
 };
 
 __host__ __device__ constexpr int tc_stage_bytes(int nt) { return TC_M * TC_BK * 2 + nt * TC_BK * 2; }
@@ -120,6 +122,40 @@ __global__ void __launch_bounds__(1024) tc_argmax_kernel(const float* logits, in
     for (int w = 1; w < 32; ++w)
       if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
     ctl->token = bi;
+  }
+}
+
+// sparse MoE prefill: rows of the gathered buffers per expert.  One block: count -> 128-row-aligned offsets -> assign rows.
+// exp_info[2e] = first row of expert e, [2e+1] = its 128-row tiles, [2E] = total rows; row_of[2s+k] = row of token s's k-th
+// expert (ascending index); row_token[row] = token or -1 (padding).
+__global__ void __launch_bounds__(1024) moe_plan_kernel(const int* route_e, int S, int E, int rows_max, int* row_of, int* row_token,
+                                                        int* exp_info) {
+  __shared__ int cnt[8], off[9];
+  if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * S; i += 1024) atomicAdd(&cnt[route_e[i]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    off[0] = 0;
+    for (int x = 0; x < E; ++x) {
+      const int tiles = (cnt[x] + TC_M - 1) / TC_M;
+      off[x + 1] = off[x] + tiles * TC_M;
+      exp_info[2 * x] = off[x];
+      exp_info[2 * x + 1] = tiles;
+    }
+    exp_info[2 * E] = off[E];
+  }
+  for (int r = threadIdx.x; r < rows_max; r += 1024) row_token[r] = -1;
+  __syncthreads();
+  // rows inside an expert block in token order (deterministic): one warp-free serial pass per expert would be slow, so each
+  // thread ranks its own pair by counting earlier pairs of the same expert
+  for (int i = threadIdx.x; i < 2 * S; i += 1024) {
+    const int x = route_e[i];
+    int rank = 0;
+    for (int j = 0; j < i; ++j) rank += (route_e[j] == x) ? 1 : 0;
+    const int r = off[x] + rank;
+    row_of[i] = r;
+    row_token[r] = i >> 1;
   }
 }
 
