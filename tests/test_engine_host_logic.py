@@ -33,6 +33,8 @@ class FakeNative:
 
   def load_dir(self, d, a, b): self.start, self.end = a, b; self.calls.append(("load", a, b))
   def begin_request(self, n): self.calls.append(("begin", n))
+  def begin_batch(self, n, b): self.calls.append(("begin_batch", n, b))
+  def select_request(self, r): self.calls.append(("select", r))
   def close(self): self.calls.append(("close",))
 
   def forward(self, x, pos0):
@@ -84,6 +86,32 @@ def test_ndim_and_position_protocol(model_dir):
     assert n0.calls[3] == ("forward", 2, (1, 1), 5) and n1.calls[3] == ("forward", 3, (1, 1, 512), 5)
     with pytest.raises(ValueError):
       await e0.infer_tensor("r", s0, np.zeros(3), None)
+  asyncio.run(run())
+
+
+def test_concurrent_request_ids_get_their_own_kv_slot(model_dir):
+  """max_concurrent_requests > 1: interleaved request ids are routed to distinct KV slots (select_request before every
+  forward), the least recently used request is evicted when the slots run out, and an evicted request fails loudly."""
+  async def run():
+    e = B200ShardInferenceEngine(LocalDirDownloader({NAME: model_dir}), device=0, native_factory=FakeNative,
+                                 max_concurrent_requests=2, max_total_len=64)
+    sh = Shard(NAME, 0, 3, 4)
+    ids = np.arange(4, dtype=np.int64).reshape(1, 4)
+    _, sa = await e.infer_tensor("a", sh, ids, None)
+    _, sb = await e.infer_tensor("b", sh, ids, None)
+    _, sa = await e.infer_tensor("a", sh, ids[:, :1], sa)
+    _, sb = await e.infer_tensor("b", sh, ids[:, :1], sb)
+    calls = [c for c in e.native.calls if c[0] in ("begin_batch", "select", "forward")]
+    assert calls[0] == ("begin_batch", 4 + 1024, 2)                       # one allocation for both slots
+    assert [c[1] for c in calls if c[0] == "select"] == [0, 1, 0, 1]
+    assert [c[3] for c in calls if c[0] == "forward"] == [0, 0, 4, 4] and sa == sb == {"curr_pos": 5}
+    _, sc = await e.infer_tensor("c", sh, ids, None)                      # third request: evicts "a" (least recently used)
+    assert [c[1] for c in e.native.calls if c[0] == "select"][-1] == 0
+    with pytest.raises(RuntimeError, match="no KV cache"):
+      await e.infer_tensor("a", sh, ids[:, :1], sa)
+    e.release_request("b")
+    _, sd = await e.infer_tensor("d", sh, ids, None)                      # takes the slot "b" released
+    assert [c[1] for c in e.native.calls if c[0] == "select"][-1] == 1
   asyncio.run(run())
 
 

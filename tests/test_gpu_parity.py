@@ -86,7 +86,7 @@ def _api_generate(engines, prompt, n_gen, force_ids=None, max_len=None):
 
 
 @pytest.mark.parametrize("shape_name", ["tiny-llama-hd64", "tiny-llama-hd128", "tiny-llama-3.2", "tiny-llama-hd64-f16",
-                                        "tiny-llama-hd128-f16", "tiny-mixtral", "tiny-mixtral-hd128"])
+                                        "tiny-llama-hd128-f16", "tiny-mixtral", "tiny-mixtral-hd128", "tiny-mixtral-f16"])
 def test_logits_match_oracle_teacher_forced(shape_name):
   shape = PRESETS[shape_name]
   full = [(0, shape.n_layers - 1)]
@@ -312,3 +312,40 @@ def test_requests_in_flight_equal_independent_runs(split, B):
   assert np.array_equal(got2, want[::-1])
   one, _ = ring.generate(prompts[0:1], n_gen)                    # and back to a single request
   assert np.array_equal(one, want[0])
+
+
+def test_engine_api_interleaved_request_ids(tmp_path):
+  """B200ShardInferenceEngine(max_concurrent_requests=2): two request ids interleaved token by token through infer_tensor
+  give exactly the logits of the same requests run one after the other on a single-request engine."""
+  import asyncio
+  from xotorch_b200.inference.b200_engine import B200ShardInferenceEngine, LocalDirDownloader
+  from xotorch_b200.inference.shard import Shard
+  name = "tiny-llama-hd64"
+  shape = PRESETS[name]
+  d = write_hf_dir(tmp_path / name, shape, 1234)
+  sh = Shard(name, 0, shape.n_layers - 1, shape.n_layers)
+  pa, pb = synth_prompt(shape.vocab, 9, seed=1), synth_prompt(shape.vocab, 14, seed=2)
+
+  async def one(engine, rid, prompt, n):
+    out, st = await engine.infer_tensor(rid, sh, prompt, None)
+    logs = [out[0].copy()]
+    for _ in range(n - 1):
+      tok = np.argmax(out[0]).reshape(1, 1).astype(np.int64)
+      out, st = await engine.infer_tensor(rid, sh, tok, st)
+      logs.append(out[0].copy())
+    return np.stack(logs)
+
+  async def run():
+    single = B200ShardInferenceEngine(LocalDirDownloader({name: d}), device=0)
+    want_a, want_b = await one(single, "a", pa, 6), await one(single, "b", pb, 6)
+    multi = B200ShardInferenceEngine(LocalDirDownloader({name: d}), device=0, max_concurrent_requests=2, max_total_len=64)
+    oa, sa = await multi.infer_tensor("a", sh, pa, None)
+    ob, sb = await multi.infer_tensor("b", sh, pb, None)
+    got_a, got_b = [oa[0].copy()], [ob[0].copy()]
+    for _ in range(5):                                     # strictly alternating decode steps of the two requests
+      oa, sa = await multi.infer_tensor("a", sh, np.argmax(oa[0]).reshape(1, 1).astype(np.int64), sa)
+      ob, sb = await multi.infer_tensor("b", sh, np.argmax(ob[0]).reshape(1, 1).astype(np.int64), sb)
+      got_a.append(oa[0].copy()); got_b.append(ob[0].copy())
+    assert np.array_equal(np.stack(got_a), want_a) and np.array_equal(np.stack(got_b), want_b)
+  asyncio.run(run())
+

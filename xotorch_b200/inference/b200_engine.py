@@ -65,7 +65,12 @@ class LocalDirDownloader:
 
 class B200ShardInferenceEngine(InferenceEngine):
   def __init__(self, shard_downloader=None, device: Optional[int] = None,
-               native_factory: Optional[Callable] = None):
+               native_factory: Optional[Callable] = None, max_concurrent_requests: int = 1,
+               max_total_len: Optional[int] = None):
+    """max_concurrent_requests > 1: the engine keeps that many KV caches and serves interleaved `request_id`s (the
+    reference's Node tracks requests individually, but its engine is single-request: `self.request_id` latched at
+    sharded_inference_engine.py:250, one KV cache, so two overlapping requests corrupt each other).  `max_total_len`
+    then fixes the KV capacity per request (default: first prompt + 1024, like the reference's prompt + max_generated)."""
     self.shard: Optional[Shard] = None
     self.shard_downloader = shard_downloader if shard_downloader is not None else LocalDirDownloader()
     self.tokenizer = None
@@ -82,6 +87,9 @@ class B200ShardInferenceEngine(InferenceEngine):
     self._native_factory = native_factory                   # tests inject a stand-in; default = the CUDA library
     self._kv_capacity = 0
     self._pos = 0
+    self.max_concurrent_requests = int(max_concurrent_requests)
+    self.max_total_len = max_total_len
+    self._slots: Dict[str, int] = {}                        # request_id -> KV slot, in least-recently-used order
     import torch
     self._rng = torch.Generator(device="cpu")
     self._rng.manual_seed(1234)                             # sharded_inference_engine.py:67-69
@@ -153,13 +161,33 @@ class B200ShardInferenceEngine(InferenceEngine):
     self.request_id = request_id
 
     def step():
+      need = max(n + MAX_GENERATED_TOKENS, int((inference_state or {}).get("max_total_len", 0)))
+      if self.max_concurrent_requests <= 1:
+        if start_pos == 0:
+          self.native.begin_request(need)
+          self._kv_capacity = need
+        return self.native.forward(input_data, start_pos)
+      # several requests in flight: one KV slot per request id (xotb200_begin_batch / xotb200_select_request)
       if start_pos == 0:
-        need = n + MAX_GENERATED_TOKENS
-        extra = int((inference_state or {}).get("max_total_len", 0))
-        self.native.begin_request(max(need, extra))
-        self._kv_capacity = max(need, extra)
-      out = self.native.forward(input_data, start_pos)
-      return out
+        if self._kv_capacity == 0:
+          self._kv_capacity = max(need, int(self.max_total_len or 0))
+          self.native.begin_batch(self._kv_capacity, self.max_concurrent_requests)
+          self._slots.clear()
+        if need - MAX_GENERATED_TOKENS > self._kv_capacity:
+          raise RuntimeError(f"prompt of {n} tokens exceeds the per-request KV capacity {self._kv_capacity} (max_total_len)")
+        if request_id not in self._slots:
+          if len(self._slots) >= self.max_concurrent_requests:   # evict the least recently used request's cache
+            self._slots.pop(next(iter(self._slots)))
+          used = set(self._slots.values())
+          self._slots[request_id] = next(i for i in range(self.max_concurrent_requests) if i not in used)
+      elif request_id not in self._slots:
+        raise RuntimeError(f"request {request_id!r} has no KV cache on this engine (evicted or never started here)")
+      slot = self._slots.pop(request_id)
+      self._slots[request_id] = slot                             # most recently used last
+      if start_pos + n > self._kv_capacity:
+        raise RuntimeError(f"request {request_id!r} reached the KV capacity {self._kv_capacity}")
+      self.native.select_request(slot)
+      return self.native.forward(input_data, start_pos)
     out = await self._run(step)
     if shard.is_last_layer():
       new_pos = n if start_pos == 0 else start_pos + 1
@@ -167,6 +195,10 @@ class B200ShardInferenceEngine(InferenceEngine):
       new_pos = start_pos
     self._pos = new_pos
     return out, {"curr_pos": new_pos}
+
+  def release_request(self, request_id: str) -> None:
+    """Free the KV slot of a finished request (Node knows when a request ends: node.py:119-147)."""
+    self._slots.pop(request_id, None)
 
   async def load_checkpoint(self, shard: Shard, path: str):
     await self.ensure_shard(shard)                          # sharded_inference_engine.py:423-424

@@ -111,6 +111,8 @@ PRESETS: Dict[str, ModelShape] = {
   "tiny-mixtral": ModelShape("tiny-mixtral", 4, 512, 1024, 8, 2, 64, 2048, rope_theta=1e6, max_pos=2048, n_experts=8, top_k=2),
   "tiny-mixtral-hd128": ModelShape("tiny-mixtral-hd128", 3, 1024, 2048, 8, 2, 128, 4096, rope_theta=1e6, max_pos=2048,
                                    n_experts=4, top_k=2),
+  "tiny-mixtral-f16": ModelShape("tiny-mixtral-f16", 4, 512, 1024, 8, 2, 64, 2048, rope_theta=1e6, max_pos=2048, n_experts=8,
+                                 top_k=2, dtype="float16"),
   "mixtral-8x7b": ModelShape("mixtral-8x7b", 32, 4096, 14336, 32, 8, 128, 32000, rope_theta=1e6, max_pos=32768,
                              n_experts=8, top_k=2),
   # same dimensions with bf16 weights: what the engine runs today (fp16 weights are not implemented yet)
