@@ -235,6 +235,10 @@ def run_b200(args):
     """128-token prefill through the host-buffer API; hidden state handed over per shard (bytes = 2*S*D algorithmic)."""
     return ring.prefill(prompt, max_len)
 
+  def prefill_dev():
+    """the same prefill with the hidden state handed over GPU to GPU (NCCL send/recv of the 16-bit [S, D] tensor)"""
+    return ring.prefill_device(prompt, max_len)
+
   def ring_decode(n_steps: int):
     """device-resident ring: last shard seeds shard 0 with the first generated token, then ONE persistent kernel/rank."""
     torch.cuda.synchronize()
@@ -254,6 +258,10 @@ def run_b200(args):
 
   # ---- warm-up requests ----
   prefill_ms = None
+  prefill_dev_ms = None
+  if n > 1:                                     # GPU-to-GPU prefill hop (not part of any timed region): measured once, warm
+    for _ in range(2):
+      barrier(); t0 = time.perf_counter(); prefill_dev(); barrier(); prefill_dev_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
   for _ in range(max(args.warmup, 0)):
     t0 = time.perf_counter(); prefill(); barrier(); prefill_ms = (time.perf_counter() - t0) * 1e3
     ring_decode(N_GEN)
@@ -370,7 +378,8 @@ def run_b200(args):
                              f"{N_GEN} generated, batch 1, greedy; step = one request, decode phase timed",
                  "shards": n, "layers_per_shard": (b - a + 1), "partitioning": "ring, equal HBM",
                  "l2_policy": f"inputs larger than L2 ({step_bytes_total / 1e9:.1f} GB of weights + KV streamed per token vs 126 MB L2)",
-                 "prefill_ms_host_api": round(prefill_ms, 1), "first_ids": first_ids,
+                 "prefill_ms_host_api": round(prefill_ms, 1),
+                 "prefill_ms_device_hop": None if prefill_dev_ms is None else round(prefill_dev_ms, 1), "first_ids": first_ids,
                  "ring_ids_equal_api_ids": ids_match_api},
       "clocks": clocks, "gpu_launches": int(gpu_launches),
       "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

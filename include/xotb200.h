@@ -106,6 +106,13 @@ int xotb200_select_request(xotb200_engine* e, int request);
  *                        lowest-index argmax is stored for xotb200_last_token(). ---- */
 int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidden_f32, int n_tokens, int pos0,
                     float* out_f32);
+/* The same step with the hidden state left in DEVICE memory on both sides, 16-bit in the engine's dtype ([n_tokens, dim]):
+ * the payload of PeerHandle.send_tensor (grpc_peer_handle.py:111-130) becomes 2*S*D bytes that the caller moves GPU to GPU
+ * (NCCL send/recv, cudaMemcpyPeerAsync) — bit-identical to the fp32 wire because 16-bit -> f32 -> 16-bit is exact.
+ * hidden_dev / out_hidden_dev are device pointers valid on the engine's device (the caller has made the input visible:
+ * stream-synchronised); out_hidden_dev is written when the call returns.  Last shard: logits_f32 (host) as in xotb200_forward. */
+int xotb200_forward_device(xotb200_engine* e, const int32_t* tokens, const void* hidden_dev, int n_tokens, int pos0,
+                           void* out_hidden_dev, float* logits_f32);
 /* lowest-index argmax of the most recent last-shard logits (on-device "greedy"; sharded_inference_engine.py:208-228 at temp 0) */
 int xotb200_last_token(xotb200_engine* e, int32_t* token);
 

@@ -349,3 +349,28 @@ def test_engine_api_interleaved_request_ids(tmp_path):
     assert np.array_equal(np.stack(got_a), want_a) and np.array_equal(np.stack(got_b), want_b)
   asyncio.run(run())
 
+
+@pytest.mark.parametrize("shape_name", ["tiny-llama-hd64", "tiny-llama-hd64-f16"])
+def test_forward_device_equals_host_buffer_forward(shape_name):
+  """xotb200_forward_device (hidden state handed over in device memory, 16-bit) == xotb200_forward (fp32 host arrays)."""
+  import torch
+  shape = PRESETS[shape_name]
+  nl = shape.n_layers
+  prompt = synth_prompt(shape.vocab, 150)
+  a, b = _native(shape_name, [(0, 1), (2, nl - 1)])
+  for e in (a, b):
+    e.begin_request(200)
+  want = b.forward(a.forward(prompt, 0), 0)
+  want2 = b.forward(a.forward(prompt[:, :1], 150), 150)
+  a2, b2 = _native(shape_name, [(0, 1), (2, nl - 1)])
+  for e in (a2, b2):
+    e.begin_request(200)
+  dt = torch.float16 if shape.dtype == "float16" else torch.bfloat16
+  h = torch.empty((150, shape.dim), dtype=dt, device="cuda:0")
+  assert a2.forward_device(prompt, None, 150, 0, h.data_ptr()) is None
+  got = b2.forward_device(None, h.data_ptr(), 150, 0, None)
+  h1 = torch.empty((1, shape.dim), dtype=dt, device="cuda:0")
+  a2.forward_device(prompt[:, :1], None, 1, 150, h1.data_ptr())
+  got2 = b2.forward_device(None, h1.data_ptr(), 1, 150, None)
+  assert np.array_equal(got, want) and np.array_equal(got2, want2)
+

@@ -50,6 +50,7 @@ _SIGS = {
   "xotb200_begin_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
   "xotb200_select_request": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+  "xotb200_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
   "xotb200_last_token": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
   "xotb200_inbox_export": (C.c_int, [C.c_void_p, C.c_void_p]),
   "xotb200_link_next_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),

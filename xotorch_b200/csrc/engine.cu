@@ -1082,6 +1082,43 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
   return 0;
 }
 
+// Same step with the hidden state staying in device memory on both sides (16-bit, the engine's dtype): the hop between
+// shards is then 2*S*D bytes moved GPU to GPU by the caller (NCCL send/recv, cudaMemcpyPeer) instead of a host round trip.
+int xotb200_forward_device(xotb200_engine* e, const int32_t* tokens, const void* hidden_dev, int n_tokens, int pos0,
+                           void* out_hidden_dev, float* logits_f32) {
+  REQUIRE(e && e->start >= 0, "no shard set");
+  REQUIRE((tokens != nullptr) != (hidden_dev != nullptr), "exactly one of tokens / hidden must be given");
+  REQUIRE((tokens != nullptr) == e->first, "%s shard expects %s", e->first ? "first" : "non-first",
+          e->first ? "token ids" : "a hidden state");
+  REQUIRE(n_tokens >= 1 && pos0 >= 0, "bad n_tokens/pos0");
+  REQUIRE(e->L > 0, "begin_request was not called");
+  REQUIRE(pos0 + n_tokens <= e->L, "KV cache overflow: pos0 %d + n %d > capacity %d", pos0, n_tokens, e->L);
+  REQUIRE(e->last ? (logits_f32 != nullptr) : (out_hidden_dev != nullptr), "null output");
+  if (int rc = xotb200_check_loaded(e)) return rc;
+  CK(cudaSetDevice(e->device));
+  if (int rc = ensure_staging(e, n_tokens)) return rc;
+  const size_t D = e->cfg.dim;
+  cudaStream_t st = e->stream;
+  if (tokens) {
+    for (int i = 0; i < n_tokens; ++i)
+      REQUIRE(tokens[i] >= 0 && tokens[i] < e->cfg.vocab, "token id %d out of range", tokens[i]);
+    CK(cudaMemcpyAsync(e->stage_tokens, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    CK(cudaMemcpyAsync(e->stage_in, hidden_dev, (size_t)n_tokens * D * 2, cudaMemcpyDeviceToDevice, st));
+  }
+  const bool use_tc = e->prefill_mode == 2 || (e->prefill_mode == 0 && n_tokens >= 8);
+  if (use_tc) {
+    if (int rc = prefill_tc(e, n_tokens, pos0, st)) return rc;
+  } else {
+    if (int rc = launch_mega(e, 1, n_tokens, 0, pos0, st)) return rc;
+  }
+  if (e->last) CK(cudaMemcpyAsync(logits_f32, e->logits, (size_t)e->cfg.vocab * 4, cudaMemcpyDeviceToHost, st));
+  else CK(cudaMemcpyAsync(out_hidden_dev, e->stage_out, (size_t)n_tokens * D * 2, cudaMemcpyDeviceToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  e->have_result = true;
+  return 0;
+}
+
 int xotb200_last_token(xotb200_engine* e, int32_t* token) {
   REQUIRE(e && token, "null argument");
   REQUIRE(e->last && e->have_result, "no last-shard result available");

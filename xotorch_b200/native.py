@@ -131,6 +131,21 @@ class NativeShard:
     check(self.lib.xotb200_forward(self.h, tok_p, hid_p, n, int(pos0), out.ctypes.data_as(C.c_void_p)))
     return out
 
+  def forward_device(self, ids: Optional[np.ndarray], hidden_dev_ptr: Optional[int], n_tokens: int, pos0: int,
+                     out_dev_ptr: Optional[int]) -> Optional[np.ndarray]:
+    """The same step with the hidden state in DEVICE memory (16-bit, engine dtype, [n_tokens, dim]) on both sides:
+    `hidden_dev_ptr` / `out_dev_ptr` are raw device pointers (e.g. torch.Tensor.data_ptr() of a tensor on this GPU whose
+    producer stream has been synchronised).  Returns the logits [1, V] on the last shard, else None."""
+    tok_p = None
+    if ids is not None:
+      ids = np.ascontiguousarray(ids, dtype=np.int32)
+      tok_p = ids.ctypes.data_as(C.c_void_p)
+    logits = np.empty((1, self.cfg.vocab), dtype=np.float32) if self.is_last else None
+    check(self.lib.xotb200_forward_device(self.h, tok_p, C.c_void_p(hidden_dev_ptr) if hidden_dev_ptr else None, int(n_tokens),
+                                          int(pos0), C.c_void_p(out_dev_ptr) if out_dev_ptr else None,
+                                          logits.ctypes.data_as(C.c_void_p) if logits is not None else None))
+    return logits
+
   def last_token(self) -> int:
     t = C.c_int32()
     check(self.lib.xotb200_last_token(self.h, C.byref(t)))

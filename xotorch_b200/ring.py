@@ -155,6 +155,31 @@ class DistributedRing:
     ids = np.asarray(prompt_ids, dtype=np.int32).reshape(1, -1)
     return self.forward_through_ring(ids if self.first else None, ids.shape[1], 0)
 
+  def prefill_device(self, prompt_ids: np.ndarray, max_total_len: int, begin: bool = True) -> Optional[np.ndarray]:
+    """Prefill with a GPU-to-GPU hop: the 16-bit hidden state [S, D] goes from `xotb200_forward_device` of one rank to the
+    next rank's by NCCL send/recv over NVLink (2*S*D bytes, the algorithmic size of the hop) — no host staging.
+    Rank 0 passes the ids; the last rank returns the logits [1, V]; every other rank returns None."""
+    import torch
+    if begin:
+      self.native.begin_request(max_total_len)
+    ids = np.asarray(prompt_ids, dtype=np.int32).reshape(1, -1)
+    S = ids.shape[1]
+    if self.world == 1:
+      return self.native.forward(ids, 0)
+    dt = torch.float16 if self.native.cfg.dtype == 1 else torch.bfloat16
+    h = out = None
+    if not self.first:
+      h = torch.empty((S, self.dim), dtype=dt, device=self.comm_device)
+      self.dist.recv(h, self.prev)
+      torch.cuda.current_stream().synchronize()            # the engine runs on its own stream
+    if not self.last:
+      out = torch.empty((S, self.dim), dtype=dt, device=self.comm_device)
+    logits = self.native.forward_device(ids if self.first else None, h.data_ptr() if h is not None else None, S, 0,
+                                        out.data_ptr() if out is not None else None)
+    if out is not None:
+      self.dist.send(out, self.next)
+    return logits
+
   def api_decode(self, first_token: int, pos0: int, n_gen: int) -> List[int]:
     """Greedy decode through the host API, token by token (what Node drives): returns the n_gen ids on every rank."""
     tok, pos, out = first_token, pos0, []
