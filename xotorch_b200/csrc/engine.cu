@@ -126,7 +126,7 @@ struct xotb200_engine {
   unsigned int* tickets = nullptr;  // [Hkv] attention + [1] step end
   float* cta_best_val = nullptr;
   int* cta_best_idx = nullptr;
-  int nsplit = 1;
+  int nsplit = 1, nsplit_min = 1;
   StepCtl* ctl = nullptr;
   InboxHdr* inbox = nullptr;
   InboxHdr* next_inbox = nullptr;
@@ -251,6 +251,10 @@ static int prepare_mega(xotb200_engine* e) {
   e->mega_grid = e->sm_count;   // one CTA per SM, all co-resident (cooperative launch checks it)
   if (e->cta_limit > 0) e->mega_grid = std::min(e->mega_grid, e->cta_limit);
   e->nsplit = std::max(1, std::min(32, e->mega_grid / c.n_kv_heads));
+  e->nsplit_min = std::min(e->nsplit, 12);
+  if (const char* v = getenv("XOTB200_NSPLIT")) e->nsplit = std::max(1, std::min(e->nsplit, atoi(v)));   // tuning hooks
+  if (const char* v = getenv("XOTB200_NSPLIT_MIN")) e->nsplit_min = std::max(1, atoi(v));
+  e->nsplit_min = std::min(e->nsplit_min, e->nsplit);
   return 0;
 }
 
@@ -267,7 +271,7 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.first = e->first ? 1 : 0; a.last = e->last ? 1 : 0;
   a.x = e->x; a.q = e->q; a.attn_out = e->attn_out; a.act = e->act; a.logits = e->logits;
   a.part_ml = e->part_ml; a.part_acc = e->part_acc; a.tickets = e->tickets;
-  a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit;
+  a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit; a.nsplit_min = e->nsplit_min;
   a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
   a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;

@@ -62,7 +62,7 @@ struct MegaArgs {
   unsigned int* tickets;     // [Hkv]
   float* cta_best_val;
   int* cta_best_idx;
-  int nsplit;
+  int nsplit, nsplit_min;   // context splits per kv head: upper bound (CTAs / kv heads) and the count used for short contexts
   StepCtl* ctl;
   InboxHdr *inbox, *next_inbox;
   int* tokens_log;
