@@ -374,9 +374,41 @@ static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CU
   e->launches++;
   return 0;
 }
+// persistent variant (one CTA per SM, two TMEM accumulators): used when a launch has more output tiles than SMs
+template <int NT, int NS>
+static int launch_tc_gemm_persistent(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
+                                     int tiles, cudaStream_t st) {
+  void (*fn)(CUtensorMap, CUtensorMap, TcGemmArgs) = nullptr;
+  const bool f16 = e->cfg.dtype == XOTB200_DTYPE_F16;
+  switch (epi) {
+    case TCE_STORE: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_STORE, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_STORE, NS>; break;
+    case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_RESID, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_RESID, NS>; break;
+    default: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_HEAD_LAST, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_HEAD_LAST, NS>; break;
+  }
+  static std::map<std::pair<int, void*>, bool> attr_done;
+  auto key = std::make_pair(e->device, (void*)fn);
+  if (!attr_done.count(key)) {
+    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT, NS)));
+    attr_done[key] = true;
+  }
+  fn<<<std::min(tiles, e->sm_count), TC_THREADS, tc_smem_bytes(NT, NS), st>>>(tmA, tmB, a);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
 static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi, TcCfg c,
                           cudaStream_t st) {
   REQUIRE(a.N % c.nt == 0 && a.K % TC_BK == 0, "tensor-core GEMM needs N %% %d == 0 and K %% 64 == 0 (N=%d K=%d)", c.nt, a.N, a.K);
+  {
+    static const bool persist = !(getenv("XOTB200_TC_PERSIST") && atoi(getenv("XOTB200_TC_PERSIST")) == 0);
+    const int mt = a.grid_m > 0 ? a.grid_m : (epi == TCE_HEAD_LAST ? 1 : (a.S + TC_M - 1) / TC_M - a.mt0);
+    const int tiles = mt * (a.N / c.nt);
+    if (persist && tiles > e->sm_count) {
+      if (c.nt == 256 && c.ns == 4) return launch_tc_gemm_persistent<256, 4>(e, tmA, tmB, a, epi, tiles, st);
+      if (c.nt == 128 && (c.ns == 6 || c.ns == 3)) return launch_tc_gemm_persistent<128, 6>(e, tmA, tmB, a, epi, tiles, st);
+    }
+  }
 #define TC_CASE(NT_, NS_) if (c.nt == NT_ && c.ns == NS_) return launch_tc_gemm_nt<NT_, NS_>(e, tmA, tmB, a, epi, st)
   TC_CASE(32, 8); TC_CASE(64, 8); TC_CASE(64, 4); TC_CASE(128, 6); TC_CASE(128, 3); TC_CASE(256, 4); TC_CASE(256, 2);
 #undef TC_CASE
