@@ -31,6 +31,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_PROMPT, N_GEN = 128, 512
+NCU_TRAFFIC_PER_TOKEN = int((720.96e9 + 85.0e6) / 48)   # measured DRAM traffic of the decode kernel per token (see roofline.traffic_note)
 MODEL = "llama-3-8b"
 SEED = 1234
 
@@ -386,7 +387,10 @@ def run_b200(args):
               "how": "NativeShard.forward (== InferenceEngine.infer_tensor) per token with host ndarrays; host argmax; "
                      + ("NCCL send/recv of the fp32 hidden state between ranks" if n > 1 else "single shard")},
       "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                   "traffic": None, "peak_source": peak_src,
+                   "traffic": NCU_TRAFFIC_PER_TOKEN if (MODEL == "llama-3-8b" and n == 1) else None,
+                   "traffic_note": "bytes per token = (dram__bytes_read.sum + dram__bytes_write.sum) / 48 tokens of one persistent-kernel launch, "
+                                   "ncu --set full at context 128..175 (profiles/r1_megakernel_ncu_full_metrics.txt): equals the algorithmic bytes, no re-reads",
+                   "peak_source": peak_src,
                    "kernel": "whole decode step (all shard kernels of one token), algorithmic bytes = weights once + valid KV",
                    "bytes_per_token": step_bytes_total},
       "hop": hop, "pipelined": pipelined, "cpu_baseline": cpu,
