@@ -1,7 +1,8 @@
-// engine.cu — host side of libxotb200.so: engine object, weight layout + strict loader, request state, the step
-// launcher (direct mode and CUDA-graph ring mode) and the C ABI declared in include/xotb200.h.
+// engine.cu — host side of libxotb200.so: engine object, weight layout + strict loader, request state (one KV cache per
+// request in flight), the launchers (persistent decode kernel in direct and ring mode, tensor-core prefill incl. the
+// sparse-MoE plan) and the C ABI declared in include/xotb200.h.
 //
-// HBM layout of a shard (all bf16, 256-byte aligned, execution order so one decode step walks HBM linearly).
+// HBM layout of a shard (16-bit weights: bf16 or IEEE half, 256-byte aligned, execution order so one decode step walks HBM linearly).
 // Every streamed matrix [N, K] is stored as K-panels [K/TK][N][TK]: any 8 consecutive rows of one K chunk — one ring
 // stage of the persistent kernel — are contiguous, so a stage is ONE TMA bulk copy of up to 32 KiB (the single producer
 // thread can issue only ~14 M bulk copies/s; with 4 KiB row-wise copies it could not outrun HBM).
@@ -10,8 +11,9 @@
 //       /root/reference/xotorch/inference/llm_utils.py:175-183) so a RoPE pair is two ADJACENT rows and the rotation
 //       fuses into the GEMV epilogue; v rows unchanged.
 //     Wgu rows: gate_m, up_m interleaved so SwiGLU fuses into the epilogue.
-//   first shard: embed[V, D];  last shard: final_norm[D] | lm_head[V, D] (aliases embed when tied).
-//   KV cache: [local_layer][k|v][Hkv][L][hd] (same [Hkv, L, hd] order as torchtune KVCache).
+//     sparse MoE (Mixtral): Wgu / Wdown hold the E experts back to back (each in the same K-panel layout) + router[E, D].
+//   first shard: embed[V, D];  last shard: final_norm[D] | lm_head[V, D] (a second, K-panelled copy of embed when tied).
+//   KV cache: [request][local_layer][k|v][Hkv][L][hd] (same [Hkv, L, hd] order as torchtune KVCache).
 #include <cuda_runtime.h>
 #include <dirent.h>
 #include <fcntl.h>

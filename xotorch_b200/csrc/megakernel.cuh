@@ -8,16 +8,20 @@
 // Why one kernel: at batch 1 every matrix is read exactly once per token, so the step is HBM-bound, but one
 // matrix is only 5-35 us of HBM time and a kernel boundary costs several us of drained memory pipe.  Here the
 // weight stream never stops:
-//   * grid = one CTA per SM, 8 warps; every warp owns a private ring of S shared-memory stages fed by TMA bulk
-//     copies (cp.async.bulk, mbarrier complete_tx) and walks ONE tile list that spans all ops, layers and steps.
-//     A stage is refilled as soon as it is consumed, so while a CTA waits at a grid barrier or does attention its
-//     next weights are already in flight (weights never depend on activations).
+//   * grid = one CTA per SM, 10 warps: a TMA producer warp, 8 K-split consumer warps, an epilogue warp.  The producer
+//     walks ONE tile list that spans all ops, layers and steps and feeds a CTA-level ring of 12 x 16 KiB shared-memory
+//     stages with one bulk copy per stage (cp.async.bulk + mbarrier complete_tx; K-panel weight layout).  A stage is
+//     refilled as soon as it is consumed, so while a CTA waits at a grid barrier or does attention its next weights
+//     are already in flight (dense weights never depend on activations; sparse-MoE expert weights wait for the router).
+//   * every consumer warp takes its 256 columns of every stage (packed FFMA2), partial sums go through a 4-slot
+//     mbarrier mailbox to the epilogue warp: fixed-order reduction + fused RoPE / KV append / residual / SwiGLU / arg-max.
 //   * ops are separated by grid barriers (release/acquire on a monotonic counter); activations (<= 56 KiB) travel
-//     through L2.
-//   * the inter-shard hop is fused: the down-proj epilogue of a shard's last layer stores the bf16 hidden state
+//     through L2; attention runs between the QKV and O ops as (kv head x context split) items with a ticket merge.
+//   * the inter-shard hop is fused: the down-proj epilogue of a shard's last layer stores the 16-bit hidden state
 //     straight into the NEXT shard's inbox over NVLink (peer stores) and CTA 0 releases a flag; the next shard's
 //     CTAs acquire that flag before their first RMSNorm.  The last shard's lm_head epilogue produces the argmax
 //     token and stores it into shard 0's inbox the same way (ring closure), so no host code runs per token.
+//   * several requests can be in flight: ring step s serves request s % nreq (own KV cache, inbox slot s % (nreq+1)).
 #pragma once
 #include "kernels.cuh"
 
