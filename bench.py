@@ -306,7 +306,7 @@ def run_b200(args):
       tok = ring._bcast_token(tok)
     barrier()
     t0 = time.perf_counter()
-    out_ids = ring.api_decode(tok, N_PROMPT, N_GEN)
+    out_ids = ring.api_decode_device(tok, N_PROMPT, N_GEN)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0), out_ids
 
@@ -316,8 +316,10 @@ def run_b200(args):
     dt, e2e_ids = api_request()
     e2e_times.append(max_over_ranks(dt))
   e2e_value = N_GEN / float(np.mean(e2e_times))
-  h2d = (N_PROMPT * 4 + N_GEN * 4) if first else (N_PROMPT * D * 4 + N_GEN * D * 4)
-  d2h = ((N_GEN + 1) * V * 4) if last else (N_PROMPT * D * 4 + N_GEN * D * 4)
+  # host<->device bytes of one request, summed over the ranks: ids in on the first shard, logits out on the last (every token),
+  # plus the prompt's fp32 hidden state through the host-array API once per shard boundary
+  h2d = (N_PROMPT + N_GEN) * 4 + (n - 1) * N_PROMPT * D * 4
+  d2h = (N_GEN + 1) * V * 4 + (n - 1) * N_PROMPT * D * 4
 
   # ---- requests in flight (N>1): B = N independent batch-1 requests interleaved through the ring, so every shard is busy.
   #      Reported beside the headline, never instead of it: `value` stays the single-request metric BASELINE.json names. ----
@@ -384,8 +386,9 @@ def run_b200(args):
                  "ring_ids_equal_api_ids": ids_match_api},
       "clocks": clocks, "gpu_launches": int(gpu_launches),
       "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-              "how": "NativeShard.forward (== InferenceEngine.infer_tensor) per token with host ndarrays; host argmax; "
-                     + ("NCCL send/recv of the fp32 hidden state between ranks" if n > 1 else "single shard")},
+              "how": "one engine call per shard per token through the C ABI: token ids from host memory in, logits to host memory out, host argmax; "
+                     + ("one engine call per rank per token (xotb200_forward_device), 16-bit hidden state [1, D] rank to rank by NCCL send/recv, "
+                        "token id broadcast back" if n > 1 else "single shard: NativeShard.forward == InferenceEngine.infer_tensor with host ndarrays")},
       "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                    "traffic": NCU_TRAFFIC_PER_TOKEN if (MODEL == "llama-3-8b" and n == 1) else None,
                    "traffic_note": "bytes per token = (dram__bytes_read.sum + dram__bytes_write.sum) / 48 tokens of one persistent-kernel launch, "

@@ -194,6 +194,34 @@ class DistributedRing:
       pos += 1
     return out
 
+  def api_decode_device(self, first_token: int, pos0: int, n_gen: int) -> List[int]:
+    """`api_decode` with the hop kept on the GPUs: every rank still makes one engine call per token (token ids come from
+    host memory on the first shard, logits go back to host memory on the last — the user-visible API), but the hidden
+    state [1, D] travels rank to rank as a 16-bit device tensor (NCCL send/recv over NVLink, `xotb200_forward_device`)
+    instead of through fp32 host arrays."""
+    import torch
+    if self.world == 1:
+      return self.api_decode(first_token, pos0, n_gen)
+    dt = torch.float16 if self.native.cfg.dtype == 1 else torch.bfloat16
+    h = None if self.first else torch.empty((1, self.dim), dtype=dt, device=self.comm_device)
+    out = None if self.last else torch.empty((1, self.dim), dtype=dt, device=self.comm_device)
+    tok, pos, ids_out = first_token, pos0, []
+    for _ in range(n_gen):
+      if h is not None:
+        self.dist.recv(h, self.prev)
+        torch.cuda.current_stream().synchronize()
+      logits = self.native.forward_device(np.array([[tok]], dtype=np.int32) if self.first else None,
+                                          h.data_ptr() if h is not None else None, 1, pos,
+                                          out.data_ptr() if out is not None else None)
+      if out is not None:
+        self.dist.send(out, self.next)
+      if self.last:
+        tok = int(np.argmax(logits[0]))
+      tok = self._bcast_token(tok)              # ring closure: the id travels back to the first shard
+      ids_out.append(tok)
+      pos += 1
+    return ids_out
+
   # -- device-resident decode -------------------------------------------------------------------------------------------
   def ring_decode(self, n_steps: int, pos0: int) -> Tuple[Optional[np.ndarray], float]:
     """After a prefill: the last shard seeds shard 0's inbox with the first generated token, then every rank launches
