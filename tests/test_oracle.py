@@ -170,3 +170,24 @@ def test_position_protocol_only_last_shard_advances():
   assert h.shape == (1, 5, 512) and st == {"curr_pos": 0}
   logits, st = e1.infer_tensor("r", e1.shard, h, st)
   assert logits.shape == (1, 2048) and st == {"curr_pos": 5}
+
+
+def test_moe_sharded_equals_unsharded():
+  """the reference's contract (test_inference_engine.py:43-44) for the sparse-MoE oracle too"""
+  name = "tiny-mixtral"
+  prompt = synth_prompt(PRESETS[name].vocab, 9)
+  ids_f, log_f, _ = generate_ids([_engine(name, 0, 3)], prompt, 5)
+  ids_s, log_s, _ = generate_ids([_engine(name, 0, 0), _engine(name, 1, 2), _engine(name, 3, 3)], prompt, 5)
+  assert np.array_equal(ids_f, ids_s) and np.array_equal(log_f, log_s)
+
+
+def test_edge_cases_single_token_prompt_and_kv_capacity():
+  """a 1-token prompt is a valid prefill; running past prompt + max_generated_tokens fails loudly"""
+  name = "tiny-llama-hd64"
+  e = RefEngine(model_config_from_hf(hf_config(PRESETS[name])), synth_state_dict(PRESETS[name], 1234),
+                RefShard(name, 0, 3, 4), max_generated_tokens=3)
+  ids, logits, _ = generate_ids([e], np.array([[7]], dtype=np.int32), 4)     # positions 0..3 fit a capacity of 1 + 3
+  assert ids.shape == (4,) and np.isfinite(logits).all()
+  with pytest.raises((AssertionError, IndexError)):   # position table / mask (general_mha.py:186-196) or the cache itself run out
+    generate_ids([e], np.array([[7]], dtype=np.int32), 6)
+
