@@ -38,7 +38,7 @@ def test_tcgen05_gemm_matches_numpy(S, N, K, tk):
 
 
 @pytest.mark.parametrize("shape_name,n_prompt", [("tiny-llama-hd64", 40), ("tiny-llama-hd128", 131), ("tiny-llama-3.2", 200),
-                                                 ("tiny-llama-hd128-f16", 140), ("tiny-llama-hd64", 1100)])
+                                                 ("tiny-llama-hd128-f16", 140), ("tiny-llama-hd64", 1100), ("tiny-llama-hd128", 900)])
 def test_tc_prefill_matches_oracle_and_decode_kernel_path(shape_name, n_prompt):
   shape = PRESETS[shape_name]
   full = [(0, shape.n_layers - 1)]
