@@ -31,7 +31,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_PROMPT, N_GEN = 128, 512
-NCU_TRAFFIC_PER_TOKEN = int((720.96e9 + 85.0e6) / 48)   # measured DRAM traffic of the decode kernel per token (see roofline.traffic_note)
+TRAFFIC_FILE = ROOT / "profiles" / "r2_decode_ncu_traffic.json"   # written by tools/ncu_summarize.py from an `ncu --set full` capture of THIS build
 MODEL = "llama-3-8b"
 SEED = 1234
 
@@ -127,70 +127,105 @@ def even_partition(n_layers: int, n: int, rank: int):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline (oracle = test infrastructure; only place bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(sample_layers: int = 4, decode_steps: int = 8):
-  """Bounded sample of the SAME workload on the host cores: the 8B-shaped model cut to `sample_layers` layers + the
-  full lm_head, 128-token prefill then `decode_steps` greedy steps (median step time); the final-norm + lm_head +
-  sampler cost is timed separately in the same process, so  t_layer = (t_step - t_head) / sample_layers  and the
-  per-token time is extrapolated as  t_layer * 32 + t_head.  Returns (tokens/s, cores, description)."""
-  import dataclasses
-  import torch
-  import torch.nn.functional as F
-  from oracle.ref_engine import RefEngine, RefShard, model_config_from_hf, rms_norm
-  from oracle.synth_fast import synth_state_dict_fast
-  from xotorch_b200.synth import PRESETS, hf_config, synth_prompt
-  shape = PRESETS[MODEL]
-  cores = usable_cores()
-  torch.set_num_threads(cores)
-  sd = synth_state_dict_fast(shape, SEED, layers=range(sample_layers))
-  prompt = synth_prompt(shape.vocab, N_PROMPT)
-  sub = dataclasses.replace(shape, n_layers=sample_layers)
-  cfg = model_config_from_hf(hf_config(sub))
-  eng = RefEngine(cfg, sd, RefShard(MODEL, 0, sample_layers - 1, sample_layers))
-  logits, state = eng.infer_tensor("cpu", eng.shard, prompt.astype(np.int32), None)      # prefill (untimed)
-  tok = eng.sample(logits, temp=0.0)
-  steps = []
-  for _ in range(decode_steps):
+_CPU_ENGINE = None
+
+
+def cpu_reference_engine():
+  """The CPU restatement of the reference engine (oracle/, test infrastructure) on the SAME workload: the full-depth model
+  (all layers + lm_head, synthetic weights of the same seed), prefilled with the same 128-token prompt.  Built once per
+  process (weight synthesis is the expensive part).  Returns (engine, state after the prefill, first token, cores)."""
+  global _CPU_ENGINE
+  if _CPU_ENGINE is None:
+    import torch
+    from oracle.ref_engine import RefEngine, RefShard, model_config_from_hf
+    from oracle.synth_fast import synth_state_dict_fast
+    from xotorch_b200.synth import PRESETS, hf_config, synth_prompt
+    shape = PRESETS[MODEL]
+    cores = usable_cores()
+    torch.set_num_threads(cores)
     t0 = time.perf_counter()
-    logits, state = eng.infer_tensor("cpu", eng.shard, tok.astype(np.int32).reshape(1, 1), state)
-    tok = eng.sample(logits, temp=0.0)                                     # reference sampler at temp 0 (node.py:121)
-    steps.append(time.perf_counter() - t0)
-  heads = []
-  h = torch.randn(1, 1, shape.dim).to(torch.bfloat16)
-  for _ in range(decode_steps):
+    sd = synth_state_dict_fast(shape, SEED)
+    t_w = time.perf_counter() - t0
+    eng = RefEngine(model_config_from_hf(hf_config(shape)), sd, RefShard(MODEL, 0, shape.n_layers - 1, shape.n_layers))
+    prompt = synth_prompt(shape.vocab, N_PROMPT)
     t0 = time.perf_counter()
-    with torch.inference_mode():
-      lg = F.linear(rms_norm(h, eng.model.norm, cfg["norm_eps"]), eng.model.output)[:, -1].float().numpy()
-    eng.sample(lg, temp=0.0)
-    heads.append(time.perf_counter() - t0)
-  t_step, t_head = float(np.median(steps)), float(np.median(heads))
-  t_layer = max(t_step - t_head, 0.0) / sample_layers
-  t_tok = t_layer * shape.n_layers + t_head
-  desc = (f"oracle RefEngine (bf16 CPU, KV prompt+1024, full-L masked SDPA, GQA expand, reference sampler temp 0), {MODEL} shape "
-          f"cut to {sample_layers} layers + lm_head, 128-token prefill then {decode_steps} decode steps (median {t_step * 1e3:.0f} ms/step, "
-          f"head alone {t_head * 1e3:.0f} ms); per-token time = t_layer*{shape.n_layers} + t_head")
-  return 1.0 / t_tok, cores, desc
+    logits, state = eng.infer_tensor("cpu", eng.shard, prompt.astype(np.int32), None)      # prefill (never timed)
+    tok = eng.sample(logits, temp=0.0)
+    _CPU_ENGINE = {"eng": eng, "state": state, "tok": tok, "cores": cores, "weights_s": t_w, "prefill_s": time.perf_counter() - t0,
+                   "layers": shape.n_layers}
+  return _CPU_ENGINE
+
+
+def cpu_decode_tokens(n_tokens: int) -> float:
+  """n_tokens REAL greedy decode steps at full depth on the host cores (continuing the prefilled request: KV of
+  prompt + 1024, full-length masked SDPA over the whole cache, GQA expand, fp32 logits, reference sampler at temperature 0 —
+  the per-token cost of the reference engine does not depend on the position).  Returns the wall seconds."""
+  c = cpu_reference_engine()
+  eng = c["eng"]
+  t0 = time.perf_counter()
+  for _ in range(n_tokens):
+    logits, c["state"] = eng.infer_tensor("cpu", eng.shard, c["tok"].astype(np.int32).reshape(1, 1), c["state"])
+    c["tok"] = eng.sample(logits, temp=0.0)                                # node.py:121
+  return time.perf_counter() - t0
+
+
+def cpu_sample_desc(c, n_tokens, what):
+  return (f"oracle RefEngine = CPU restatement of the reference torch engine (bf16 weights, KV prompt+1024, full-length masked SDPA, GQA expand, "
+          f"reference sampler temp 0), FULL {MODEL} shape: all {c['layers']} layers + lm_head, {N_PROMPT}-token prefill ({c['prefill_s']:.1f} s, untimed; "
+          f"weights synthesised in {c['weights_s']:.0f} s) then {n_tokens} real decode steps {what}; nothing extrapolated")
+
+
+def workload_string(dtype_name: str) -> str:
+  """one string for both arms (`config.workload`), so the driver can tell they measure the same thing"""
+  return (f"{MODEL} shape, synthetic {dtype_name} weights (seed {SEED}), {N_PROMPT}-token prompt / {N_GEN} generated, batch 1, greedy; "
+          f"metric = decode tokens/s")
 
 
 def run_reference(args):
+  """`--impl reference`: the reference's own CPU implementation of the path.  The reference engine cannot be imported
+  (torchtune is absent here and on the box), so this is the oracle port, timed on all usable host cores.
+  A step = a bounded sample of the workload: `tok_per_step` consecutive decode tokens of the full-depth model (at least 32
+  timed tokens in total); W warm-up steps, then K timed steps; value = timed tokens / timed seconds."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  t0 = time.time()
-  vals = []
-  for _ in range(max(1, min(args.steps, 2))):
-    v, cores, desc = cpu_reference_sample(sample_layers=4, decode_steps=8)
-    vals.append(v)
-  v = float(np.mean(vals))
+  from xotorch_b200.synth import PRESETS
+  t_start = time.time()
+  sh = PRESETS[MODEL]
+  need = 2 * (sh.n_layers * (sh.dim * (sh.n_heads + 2 * sh.n_kv_heads) * sh.head_dim + sh.n_heads * sh.head_dim * sh.dim
+                             + 3 * sh.dim * sh.ffn * max(1, sh.n_experts)) + 2 * sh.vocab * sh.dim)
+  try:
+    avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+  except Exception:
+    avail = 1 << 62
+  if need > 0.7 * avail:       # 70B / Mixtral: the full model does not fit the host's RAM (SURVEY.md §8d: report n/a, do not extrapolate)
+    print(json.dumps({"impl": "reference", "unavailable": f"{MODEL}: {need / 1e9:.0f} GB of weights do not fit the host's {avail / 1e9:.0f} GB of available RAM"}), flush=True)
+    return
+  steps, warm = max(1, args.steps), max(0, args.warmup)
+  tok_per_step = max(2, -(-32 // steps))
+  c = cpu_reference_engine()
+  for _ in range(warm):
+    cpu_decode_tokens(tok_per_step)
+  secs = [cpu_decode_tokens(tok_per_step) for _ in range(steps)]
+  v = steps * tok_per_step / float(np.sum(secs))
+  hop = None
+  if args.gpus > 1 and not args.no_ref_hop:
+    try:
+      from tools.ref_hop_bench import measure_reference_hop
+      hop = measure_reference_hop(dim=PRESETS[MODEL].dim)
+    except Exception as ex:                      # the comparator must never take the arm down
+      hop = {"unavailable": repr(ex)[:300]}
+  desc = cpu_sample_desc(c, steps * tok_per_step, f"in {steps} steps of {tok_per_step} tokens after {warm} warm-up steps")
   line = {
     "impl": "reference", "metric": ("Llama-3-8B" if MODEL == "llama-3-8b" else MODEL) + f" greedy decode tokens/sec ({N_PROMPT}-prompt/{N_GEN}-gen, batch 1)", "value": round(v, 4),
-    "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-    "ms_per_step": round(N_GEN / v * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-    "dtype": "bf16", "data": "synthetic",
-    "config": {"workload": f"{MODEL} shape, synthetic bf16 weights (seed {SEED}), {N_PROMPT}-token prompt / {N_GEN} generated, batch 1, CPU",
-               "shards": args.gpus},
-    "cpu_baseline": {"value": round(v, 4), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
+    "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+    "ms_per_step": round(float(np.mean(secs)) * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    "dtype": "f16" if PRESETS[MODEL].dtype == "float16" else "bf16", "data": "synthetic",
+    "config": {"workload": workload_string(PRESETS[MODEL].dtype), "shards": args.gpus,
+               "step": f"{tok_per_step} consecutive decode tokens of the full-depth model on the host CPU (bounded sample of the {N_GEN}-token generation)"},
+    "cpu_baseline": {"value": round(v, 4), "unit": "tokens/s", "cores": c["cores"], "kind": "port", "sample": desc},
     "e2e": {"value": round(v, 4), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    "wall_s": round(time.time() - t0, 1),
+    "hop": hop, "wall_s": round(time.time() - t_start, 1),
   }
   print(json.dumps(line), flush=True)
 
@@ -348,24 +383,51 @@ def run_b200(args):
     step_bytes_total = step_bytes_local
   achieved = step_bytes_total * args.steps * N_GEN / (total_ms * 1e-3) / 1e9
 
-  ids_match_api = bool(ring_tokens is not None and e2e_ids is not None and list(ring_tokens[:N_GEN - 1]) == e2e_ids[:N_GEN - 1]) if n == 1 else None
-
-  if rank == 0 or (n > 1 and last):
-    pass
-  # gather the last rank's knowledge on rank 0
+  # ---- id checks (north star: greedy ids of the same prompt must not depend on how the model is sharded or driven) ----
+  #  (1) device-resident ring == per-token API path (all N_GEN-1 ids they share);  (2) N>1: N shards == ONE shard holding all
+  #  layers, run on the last rank's GPU after the timed regions (16 GB more on a 180 GB device);  sha1 of the ring ids so the
+  #  lines of different N can be compared with each other.
+  import hashlib
+  checks = None
+  if last:
+    ring_l = [int(t) for t in ring_tokens[:N_GEN - 1]]
+    checks = {"ring_ids_equal_api_ids": bool(e2e_ids is not None and ring_l == [int(t) for t in e2e_ids[:N_GEN - 1]]),
+              "first_ids": ring_l[:8], "ids_sha1": hashlib.sha1(np.asarray(ring_l, dtype=np.int32).tobytes()).hexdigest()[:16],
+              "n_shard_ids_equal_1_shard_ids": None}
+    if n > 1 and not args.no_single_shard_check:
+      one = NativeShard(cfg, device=local)
+      one.set_shard(0, shape.n_layers - 1)
+      one.init_synthetic(SEED)
+      one.link_next_local(one)
+      one.begin_request(max_len)
+      one.forward(prompt, 0)
+      s1 = one.ring_next_step()
+      one.post_to_next(s1)
+      one.ring_launch(N_GEN, s1, N_PROMPT)
+      toks1, _ = one.ring_wait(N_GEN)
+      checks["n_shard_ids_equal_1_shard_ids"] = bool([int(t) for t in toks1[:N_GEN - 1]] == ring_l)
+      one.close()
   if n > 1:
     info = [None] * n
-    dist.all_gather_object(info, {"ring_tokens": None if ring_tokens is None else ring_tokens[:8].tolist()})
-    first_ids = [x["ring_tokens"] for x in info if x["ring_tokens"] is not None][0]
-  else:
-    first_ids = ring_tokens[:8].tolist()
+    dist.all_gather_object(info, checks)
+    checks = [x for x in info if x is not None][0]
+  first_ids = checks["first_ids"]
 
+  traffic = {}
+  if TRAFFIC_FILE.exists():
+    try:
+      traffic = json.loads(TRAFFIC_FILE.read_text())
+    except Exception:
+      traffic = {}
   if rank == 0:
     cpu = None
     if n == 1 and not args.no_cpu_baseline:
       try:
-        v, cores, desc = cpu_reference_sample(sample_layers=4, decode_steps=8)
-        cpu = {"value": round(v, 4), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc}
+        c = cpu_reference_engine()
+        cpu_decode_tokens(2)                                # warm
+        n_cpu = 16
+        v = n_cpu / cpu_decode_tokens(n_cpu)
+        cpu = {"value": round(v, 4), "unit": "tokens/s", "cores": c["cores"], "kind": "port", "sample": cpu_sample_desc(c, n_cpu, "after 2 warm-up steps")}
       except Exception as ex:  # the CPU leg must never take the GPU number down with it
         cpu = {"value": None, "unit": "tokens/s", "cores": usable_cores(), "kind": "port", "sample": f"failed: {ex!r}"}
     hop = None
@@ -377,22 +439,23 @@ def run_b200(args):
       "metric": ("Llama-3-8B" if MODEL == "llama-3-8b" else MODEL) + f" greedy decode tokens/sec ({N_PROMPT}-prompt/{N_GEN}-gen, batch 1)",
       "value": round(value, 2), "unit": "tokens/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 3),
       "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16" if shape.dtype == "float16" else "bf16", "data": "synthetic",
-      "config": {"workload": f"{MODEL} shape, synthetic {shape.dtype} weights (seed {SEED}, device-generated), {N_PROMPT}-token prompt / "
-                             f"{N_GEN} generated, batch 1, greedy; step = one request, decode phase timed",
+      "config": {"workload": workload_string(shape.dtype),
+                 "step": "one request: prefill (untimed) + the timed decode of all generated tokens; weights generated on the device",
                  "shards": n, "layers_per_shard": (b - a + 1), "partitioning": "ring, equal HBM",
                  "l2_policy": f"inputs larger than L2 ({step_bytes_total / 1e9:.1f} GB of weights + KV streamed per token vs 126 MB L2)",
                  "prefill_ms_host_api": round(prefill_ms, 1),
                  "prefill_ms_device_hop": None if prefill_dev_ms is None else round(prefill_dev_ms, 1), "first_ids": first_ids,
-                 "ring_ids_equal_api_ids": ids_match_api},
+                 "ids_sha1": checks["ids_sha1"], "ring_ids_equal_api_ids": checks["ring_ids_equal_api_ids"],
+                 "n_shard_ids_equal_1_shard_ids": checks["n_shard_ids_equal_1_shard_ids"]},
       "clocks": clocks, "gpu_launches": int(gpu_launches),
       "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
               "how": "one engine call per shard per token through the C ABI: token ids from host memory in, logits to host memory out, host argmax; "
-                     + ("one engine call per rank per token (xotb200_forward_device), 16-bit hidden state [1, D] rank to rank by NCCL send/recv, "
-                        "token id broadcast back" if n > 1 else "single shard: NativeShard.forward == InferenceEngine.infer_tensor with host ndarrays")},
+                     + ("one engine call per rank per token (xotb200_forward_hop): the producing kernel stores the 16-bit hidden state [1, D] into the "
+                        "next rank's inbox over NVLink and releases a flag the consuming kernel acquires (no NCCL, no stream sync per hop); "
+                        "only the 4-byte token id travels back through torch.distributed" if n > 1 else "single shard: NativeShard.forward == InferenceEngine.infer_tensor with host ndarrays")},
       "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                   "traffic": NCU_TRAFFIC_PER_TOKEN if (MODEL == "llama-3-8b" and n == 1) else None,
-                   "traffic_note": "bytes per token = (dram__bytes_read.sum + dram__bytes_write.sum) / 48 tokens of one persistent-kernel launch, "
-                                   "ncu --set full at context 128..175 (profiles/r1_megakernel_ncu_full_metrics.txt): equals the algorithmic bytes, no re-reads",
+                   "traffic": traffic.get("bytes_per_token") if (MODEL == "llama-3-8b" and n == 1) else None,
+                   "traffic_note": traffic.get("note"),
                    "peak_source": peak_src,
                    "kernel": "whole decode step (all shard kernels of one token), algorithmic bytes = weights once + valid KV",
                    "bytes_per_token": step_bytes_total},
@@ -411,6 +474,8 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-single-shard-check", action="store_true", help="N>1: skip re-running the request on ONE shard holding all layers")
+  ap.add_argument("--no-ref-hop", action="store_true", help="--impl reference --gpus N>1: skip the reference gRPC hop comparator")
   # the other BASELINE.json configs through the same contract (defaults = the headline config):
   #   --model llama-3-70b --gpus 8 --prompt 4096      (fp16, must shard to fit)     --model mixtral-8x7b --gpus 4
   from xotorch_b200.synth import PRESETS

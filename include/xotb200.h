@@ -113,6 +113,20 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
  * stream-synchronised); out_hidden_dev is written when the call returns.  Last shard: logits_f32 (host) as in xotb200_forward. */
 int xotb200_forward_device(xotb200_engine* e, const int32_t* tokens, const void* hidden_dev, int n_tokens, int pos0,
                            void* out_hidden_dev, float* logits_f32);
+/* The API hop — what replaces PeerHandle.send_tensor's payload (grpc_peer_handle.py:111-130; receiver grpc_server.py:73-88) when
+ * both engines sit on one NVSwitch box: the same step as xotb200_forward, one call per shard per token, but the hidden state goes
+ * from the producing kernel straight into the NEXT engine's HBM and only a hop NUMBER crosses the API (the descriptor the peer
+ * handle carries).  First shard: `tokens` (host) != NULL; other shards: seq_in = the number the previous engine's call returned.
+ * Non-last shards return the number of the hop they produced in *seq_out; the last shard writes the last position's logits to
+ * logits_f32 (host) like xotb200_forward.
+ *   n_tokens == 1 (decode): the last epilogue of the persistent kernel stores the 16-bit hidden state into the next engine's inbox
+ *     (peer store over NVLink) and releases a flag; the consuming kernel acquires it on the device.  A non-last shard's call
+ *     returns WITHOUT synchronising its stream, so the next engine's call may be issued at once: no NCCL, no host sync per hop.
+ *   n_tokens  > 1 (prompt): one peer copy of the [n_tokens, dim] block into the next engine's receive buffer; needs a same-process
+ *     link (xotb200_link_next_local).  Across processes move prompts with xotb200_forward_device + the caller's transport.
+ * At most 8 hops may be in flight on one link (the reference keeps one per request). */
+int xotb200_forward_hop(xotb200_engine* e, const int32_t* tokens, int64_t seq_in, int n_tokens, int pos0, int64_t* seq_out,
+                        float* logits_f32);
 /* lowest-index argmax of the most recent last-shard logits (on-device "greedy"; sharded_inference_engine.py:208-228 at temp 0) */
 int xotb200_last_token(xotb200_engine* e, int32_t* token);
 
@@ -134,6 +148,10 @@ int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0);
 /* Wait for the engine's stream; on the last shard copies the n_steps generated token ids (int32) to tokens_out
  * (may be NULL).  ms_out (may be NULL) = device time of the launched steps by CUDA events. */
 int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float* ms_out);
+/* First ring step number that no xotb200_post_to_next / xotb200_ring_launch on this engine has used yet.  Inbox flags hold
+ * `step + 1` and are never cleared, so step numbers must never be reused on an engine: a driver that is (re)created over
+ * existing engines, or that recovers from XOTB200_ETIMEOUT, continues from the maximum of this value over its engines. */
+int xotb200_ring_next_step(xotb200_engine* e, int* step);
 /* Per-step device timestamps (globaltimer ns) of the most recent ring run: t_in = input flag observed,
  * t_out = result posted.  Arrays of n_steps uint64 each (hop latency accounting). */
 int xotb200_ring_timestamps(xotb200_engine* e, uint64_t* t_in, uint64_t* t_out, int n_steps);

@@ -26,3 +26,19 @@ void synth_fill_bf16(uint16_t* out, uint64_t base, uint64_t start, uint64_t coun
     out[i] = f32_to_bf16_rne(prod + mean);
   }
 }
+
+/* IEEE half variant (the 70B card upstream is fp16): same counter stream, fp32 value rounded to nearest-even half.
+ * gcc >= 12 on x86-64 converts float -> _Float16 with round-to-nearest-even (checked against torch in tests/test_oracle.py). */
+void synth_fill_f16(uint16_t* out, uint64_t base, uint64_t start, uint64_t count, float scale, float mean) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)count; ++i) {
+    uint64_t z = base + start + (uint64_t)i;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    int32_t s = (int32_t)(z & 0xffff) + (int32_t)((z >> 16) & 0xffff) + (int32_t)((z >> 32) & 0xffff) + (int32_t)(z >> 48);
+    volatile float prod = (float)(s - 131070) * scale;
+    const _Float16 h = (_Float16)(prod + mean);
+    memcpy(&out[i], &h, 2);
+  }
+}

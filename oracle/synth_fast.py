@@ -18,21 +18,25 @@ def _load():
     lib = C.CDLL(str(build()))
     lib.synth_fill_bf16.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float]
     lib.synth_fill_bf16.restype = None
+    lib.synth_fill_f16.argtypes = lib.synth_fill_bf16.argtypes
+    lib.synth_fill_f16.restype = None
     _lib = lib
   return _lib
 
 
-def synth_tensor_fast(seed: int, tensor_id: int, shape, std: float, mean: float) -> torch.Tensor:
+def synth_tensor_fast(seed: int, tensor_id: int, shape, std: float, mean: float, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
   n = int(np.prod(shape))
-  out = torch.empty(n, dtype=torch.bfloat16)
+  out = torch.empty(n, dtype=dtype)
   scale = np.float32(std / synth.IH4_STD)
-  _load().synth_fill_bf16(C.c_void_p(out.data_ptr()), C.c_uint64(synth.tensor_base(seed, tensor_id)), 0, n,
+  fill = _load().synth_fill_f16 if dtype == torch.float16 else _load().synth_fill_bf16
+  fill(C.c_void_p(out.data_ptr()), C.c_uint64(synth.tensor_base(seed, tensor_id)), 0, n,
                           C.c_float(float(scale)), C.c_float(mean))
   return out.view(*shape)
 
 
 def synth_state_dict_fast(shape: synth.ModelShape, seed: int = 1234, layers: Optional[Iterable[int]] = None,
                           with_embed: bool = True, with_head: bool = True) -> Dict[str, torch.Tensor]:
-  assert shape.dtype == "bfloat16"
-  return {name: synth_tensor_fast(seed, tid, shp, std, mean)
+  assert shape.dtype in ("bfloat16", "float16")
+  dt = synth.torch_dtype(shape.dtype)
+  return {name: synth_tensor_fast(seed, tid, shp, std, mean, dt)
           for name, tid, shp, std, mean in synth.hf_tensor_specs(shape, layers, with_embed, with_head)}

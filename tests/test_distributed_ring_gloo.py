@@ -18,9 +18,10 @@ D, V, NL = 16, 64, 6
 class FakeShard:
   """Deterministic stand-in with the NativeShard surface DistributedRing uses."""
 
-  def __init__(self, rank, start, end):
+  def __init__(self, rank, start, end, mailbox=None, world=1):
     self.rank, self.start, self.end = rank, start, end
     self.linked, self.calls = None, []
+    self.mailbox, self.world, self.hop_seq = mailbox, world, 0   # a directory stands in for the next engine's inbox
 
   @property
   def is_first(self): return self.start == 0
@@ -28,7 +29,32 @@ class FakeShard:
   def is_last(self): return self.end == NL - 1
 
   def inbox_export(self): return bytes([self.rank]) * 64
-  def link_next_ipc(self, h): self.linked = h[0]
+  def ring_next_step(self): return 0
+  def link_next_ipc(self, h): self.linked = h[0]; self.hop_seq = 0
+
+  def forward_hop(self, ids, seq_in, n, pos0):
+    """xotb200_forward_hop stand-in: the hidden state goes through the mailbox directory, only hop NUMBERS cross the API"""
+    import time
+    self.calls.append(("forward_hop", None if ids is None else tuple(ids.shape), seq_in, n, pos0))
+    if ids is not None:
+      x = ids
+    else:
+      path = os.path.join(self.mailbox, f"to{self.rank}_{seq_in}.npy")
+      for _ in range(2000):
+        if os.path.exists(path):
+          break
+        time.sleep(0.005)
+      x = np.load(path)
+    out = self.forward(x, pos0)
+    self.calls.pop()                                       # the nested forward() is not an API call
+    if self.is_last:
+      return None, out
+    seq = self.hop_seq
+    self.hop_seq += 1
+    tmp = os.path.join(self.mailbox, f"tmp{self.rank}_{seq}.npy")
+    np.save(tmp, out)
+    os.replace(tmp, os.path.join(self.mailbox, f"to{(self.rank + 1) % self.world}_{seq}.npy"))
+    return seq, None
   def link_next_local(self, other): self.linked = "self"
   def begin_request(self, n): self.calls.append(("begin", n))
   def begin_batch(self, n, b): self.calls.append(("begin_batch", n, b))
@@ -61,11 +87,11 @@ def _shards(world):
   return map_partitions_to_shards(parts, NL, "m")
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mailbox):
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
   dist.init_process_group("gloo", rank=rank, world_size=world)
   sh = _shards(world)[rank]
-  native = FakeShard(rank, sh.start_layer, sh.end_layer)
+  native = FakeShard(rank, sh.start_layer, sh.end_layer, mailbox, world)
   ring = DistributedRing(native, rank, world, D, V, comm_device="cpu")
   ring.link()
   prompt = np.arange(5, dtype=np.int32).reshape(1, -1)
@@ -73,10 +99,14 @@ def _worker(rank, world, port, q):
   tok = int(np.argmax(logits[0])) if native.is_last else 0
   tok = ring._bcast_token(tok)
   ids = ring.api_decode(tok, 5, 8)
+  n_api = len(native.calls)
+  ids_hop = ring.api_decode_device(tok, 5, 8)             # the same decode with the hidden state handed over by hop number
+  hop_calls = native.calls[n_api:]
+  del native.calls[n_api:]
   ring.step = 7                                            # a batch must start at a ring step that is a multiple of B
   n0 = len(native.calls)
   bids, _ = ring.generate_batch(np.arange(15, dtype=np.int32).reshape(3, 5), 4)
-  q.put((rank, native.linked, tok, ids, native.calls[:n0], native.calls[n0:], None if bids is None else bids.tolist(), ring.step))
+  q.put((rank, native.linked, tok, ids, native.calls[:n0], native.calls[n0:], None if bids is None else bids.tolist(), ring.step, ids_hop, hop_calls))
   dist.barrier()
   dist.destroy_process_group()
 
@@ -86,7 +116,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_distributed_ring_host_logic(world):
+def test_distributed_ring_host_logic(world, tmp_path):
   # single-process truth: one shard covering all layers
   one = FakeShard(0, 0, NL - 1)
   ring1 = DistributedRing(one, 0, 1, D, V)
@@ -99,15 +129,19 @@ def test_distributed_ring_host_logic(world):
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
   port = _free_port()
-  procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+  procs = [ctx.Process(target=_worker, args=(r, world, port, q, str(tmp_path))) for r in range(world)]
   for p in procs: p.start()
   res = sorted(q.get(timeout=120) for _ in range(world))
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
-  for rank, linked, tok, ids, calls, bcalls, bids, step in res:
+  for rank, linked, tok, ids, calls, bcalls, bids, step, ids_hop, hop_calls in res:
     assert linked == (rank + 1) % world                 # each rank mapped the inbox of the NEXT rank
     assert tok == tok1 and ids == ids1                  # sharded ring == unsharded, on every rank
+    # device hop: one forward_hop per token per rank, ids only on the first shard, hop k consumed for token k elsewhere
+    assert ids_hop == ids1 and [c[0] for c in hop_calls] == ["forward_hop"] * 8
+    assert all((c[1] == (1, 1) and c[2] == -1) if rank == 0 else (c[1] is None and c[2] == k) for k, c in enumerate(hop_calls))
+    assert [c[4] for c in hop_calls] == list(range(5, 13))
     fw = [c for c in calls if c[0] == "forward"]
     assert len(fw) == 9 and fw[0][3] == 0 and [c[3] for c in fw[1:]] == list(range(5, 13))
     assert fw[0][1] == (2 if rank == 0 else 3)          # ndim protocol: ids on the first shard, hidden elsewhere

@@ -37,6 +37,18 @@ class FakeNative:
   def select_request(self, r): self.calls.append(("select", r))
   def close(self): self.calls.append(("close",))
 
+  def link_next_local(self, nxt): self.calls.append(("link", id(nxt))); self.hop_seq = 0
+
+  def forward_hop(self, ids, seq_in, n, pos0):
+    """stand-in for xotb200_forward_hop: only the protocol (who gets ids / a hop number, what comes back)"""
+    self.calls.append(("forward_hop", None if ids is None else ids.shape, seq_in, n, pos0))
+    if self.end == self.cfg["num_hidden_layers"] - 1:
+      out = np.zeros((1, self.cfg["vocab_size"]), np.float32)
+      out[0, (7 * pos0 + 3 * n) % self.cfg["vocab_size"]] = 5.0
+      return None, out
+    self.hop_seq += 1
+    return self.hop_seq - 1, None
+
   def forward(self, x, pos0):
     self.calls.append(("forward", x.ndim, x.shape, pos0))
     last = self.end == self.cfg["num_hidden_layers"] - 1
@@ -168,23 +180,19 @@ def test_sampler_is_bit_identical_to_the_oracle_restatement(model_dir):
 # ------------------------------------------------------------------------------------------------------------------
 # drop-in proof: the REFERENCE's own Node drives our engine (only where /root/reference exists: the build container)
 # ------------------------------------------------------------------------------------------------------------------
-REF = Path("/root/reference")
+from tests._refpkg import reference_root, import_reference
 
 
-@pytest.mark.skipif(not REF.exists(), reason="/root/reference is only present in the build container")
-def test_reference_node_drives_b200_engines_in_a_two_node_ring(model_dir, tmp_path, monkeypatch):
-  stub, stub_all = types.ModuleType("scapy"), types.ModuleType("scapy.all")
-  stub_all.get_if_addr = lambda *a, **k: "127.0.0.1"; stub_all.get_if_list = lambda *a, **k: []
-  monkeypatch.setitem(sys.modules, "scapy", stub); monkeypatch.setitem(sys.modules, "scapy.all", stub_all)
-  monkeypatch.syspath_prepend(str(REF))
-  monkeypatch.chdir(tmp_path)                   # device_capabilities.py writes a log into the CWD
-  monkeypatch.setattr(sys, "dont_write_bytecode", True)
+@pytest.mark.skipif(reference_root() is None, reason="the reference package is neither installed under baseline/_ref nor at /root/reference")
+@pytest.mark.parametrize("device_hop", [False, True])
+def test_reference_node_drives_b200_engines_in_a_two_node_ring(model_dir, tmp_path, monkeypatch, device_hop):
+  import_reference(monkeypatch, tmp_path)
   from xotorch.orchestration.node import Node
   from xotorch.topology.ring_memory_weighted_partitioning_strategy import RingMemoryWeightedPartitioningStrategy
   from xotorch.topology.device_capabilities import DeviceCapabilities, DeviceFlops
   from xotorch.topology.topology import Topology
   from xotorch.inference.shard import Shard as RefShard
-  from xotorch_b200.networking.nvlink_peer_handle import InProcessPeerHandle
+  from xotorch_b200.networking.nvlink_peer_handle import InProcessPeerHandle, NVLinkPeerHandle
   from unittest import mock
 
   caps = DeviceCapabilities(model="B200", chip="B200", memory=183359, flops=DeviceFlops(fp32=0, fp16=0, int8=0))
@@ -204,7 +212,11 @@ def test_reference_node_drives_b200_engines_in_a_two_node_ring(model_dir, tmp_pa
       topo.update_node(n.id, caps)
     for i, n in enumerate(nodes):
       n.topology = topo
-      n.peers = [InProcessPeerHandle(nodes[1 - i].id, nodes[1 - i], device_capabilities=caps)]
+      if device_hop:      # the handle attaches the peer's engine to the local one: hidden states stay on the device
+        n.peers = [NVLinkPeerHandle(nodes[1 - i].id, nodes[1 - i], local_engine=engines[i], device_capabilities=caps)]
+        await n.peers[0].connect()
+      else:
+        n.peers = [InProcessPeerHandle(nodes[1 - i].id, nodes[1 - i], device_capabilities=caps)]
       n.select_best_inference_engine = mock.AsyncMock()       # App. B9: upstream would swap in the torch engine
     got = []
     # the last-shard node fires on_token locally and broadcasts the delta to its peers (node.py:136-137): listen on one
@@ -220,7 +232,47 @@ def test_reference_node_drives_b200_engines_in_a_two_node_ring(model_dir, tmp_pa
     toks = [t for _, ts, _ in got for t in ts]
     assert len(toks) == 4
     # the ring really crossed both engines with the ndim protocol and the tiny state
-    c1 = [c for c in engines[1].native.calls if c[0] == "forward"]
-    c0 = [c for c in engines[0].native.calls if c[0] == "forward"]
-    assert c1[0][1] == 2 and c0[0][1] == 3 and len(c0) == 4
+    if not device_hop:
+      c1 = [c for c in engines[1].native.calls if c[0] == "forward"]
+      c0 = [c for c in engines[0].native.calls if c[0] == "forward"]
+      assert c1[0][1] == 2 and c0[0][1] == 3 and len(c0) == 4
+    else:
+      # first shard (node1): the prompt's hidden state still goes by host array once (the peer engine has not loaded its shard
+      # when the first hop is made), every later token leaves as a hop descriptor; last shard (node0) consumes hop numbers
+      c1 = [c for c in engines[1].native.calls if c[0] in ("forward", "forward_hop")]
+      c0 = [c for c in engines[0].native.calls if c[0] in ("forward", "forward_hop")]
+      assert [c[0] for c in c1] == ["forward", "forward_hop", "forward_hop", "forward_hop"]
+      assert [c[0] for c in c0] == ["forward", "forward_hop", "forward_hop", "forward_hop"]
+      assert [c[2] for c in c0[1:]] == [0, 1, 2] and all(c[1] is None for c in c0[1:])        # hop numbers in, no ids
+      assert all(c[1] == (1, 1) and c[2] == -1 for c in c1[1:])                               # ids in on the first shard
+      assert nodes[1].peers[0].sent["descriptors"] == 3 and engines[1].hop_stats["device_out"] == 3
+      assert engines[0].hop_stats["device_in"] == 3
   asyncio.run(run())
+
+
+def test_kv_capacity_is_clamped_to_the_model_context_and_chunks_advance_by_n(model_dir):
+  """prompt + 1024 must be clamped to max_position_embeddings (tiny model: 2048); a prompt that does not fit the
+  context fails loudly; a multi-token continuation chunk advances curr_pos by its length."""
+  async def run():
+    e = _engine(model_dir)
+    sh = Shard(NAME, 0, 3, 4)
+    ids = np.zeros((1, 1500), dtype=np.int64)
+    _, st = await e.infer_tensor("r", sh, ids, None)
+    assert ("begin", 2048) in e.native.calls and st == {"curr_pos": 1500}             # 1500 + 1024 > 2048 -> clamped
+    _, st = await e.infer_tensor("r", sh, ids[:, :3], st)                               # continuation chunk of 3 tokens
+    assert st == {"curr_pos": 1503}
+    with pytest.raises(RuntimeError, match="exceed the model's context"):
+      await e.infer_tensor("q", sh, np.zeros((1, 2049), dtype=np.int64), None)
+  asyncio.run(run())
+
+
+def test_cfg_from_hf_rejects_what_the_kernels_do_not_implement():
+  from xotorch_b200.native import cfg_from_hf
+  base = hf_config(SHAPE)
+  cfg_from_hf(base)
+  cfg_from_hf({**base, "rope_scaling": {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                                         "original_max_position_embeddings": 8192}})
+  for bad in ({"rope_scaling": {"type": "linear", "factor": 2.0}}, {"rope_scaling": {"rope_type": "yarn", "factor": 4.0}},
+              {"attention_bias": True}, {"mlp_bias": True}, {"hidden_act": "gelu"}, {"sliding_window": 4096}, {"model_type": "qwen2"}):
+    with pytest.raises(ValueError):
+      cfg_from_hf({**base, **bad})

@@ -64,6 +64,10 @@ def test_synth_generators_agree():
   a = synth_tensor(1234, 37, (256, 512), 0.02, 0.0)
   b = synth_tensor_fast(1234, 37, (256, 512), 0.02, 0.0)
   assert torch.equal(a, b)
+  for std in (0.02, 2e-5):   # IEEE-half twin of the generator (fp16 models), including subnormal halves
+    ah = synth_tensor(1234, 38, (128, 512), std, 0.0, torch.float16)
+    bh = synth_tensor_fast(1234, 38, (128, 512), std, 0.0, torch.float16)
+    assert torch.equal(ah.view(torch.int16), bh.view(torch.int16))
   n = synth_tensor(7, (1 << 20) + 1, (512,), 0.02, 1.0).float()
   assert abs(float(n.mean()) - 1.0) < 0.01 and 0.015 < float(n.std()) < 0.025
   assert tensor_base(1, 1) == (0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03) % (1 << 64)

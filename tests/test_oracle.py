@@ -26,10 +26,12 @@ def test_oracle_matches_committed_golden(name):
   ids, logits, gaps = generate_ids([_engine(name, 0, PRESETS[name].n_layers - 1)], g["prompt"], 24)
   # golden produced on the build container's CPU; a different CPU may flip a bf16 rounding -> tolerance, not equality
   assert np.abs(logits[:4] - g["logits"]).max() <= 0.04
-  decided = g["gaps"] > 0.08
-  assert (ids[decided] == g["ids"][decided]).all() or not np.array_equal(ids, g["ids"])
-  if np.array_equal(logits[:4], g["logits"]):
-    assert np.array_equal(ids, g["ids"])
+  # free-running ids: equal to the golden ids, or — if another CPU flipped a rounding — the FIRST step that differs must be
+  # a near-tie of the golden run (after it the two continuations legitimately differ)
+  if not np.array_equal(ids, g["ids"]):
+    first = int(np.argmax(ids != g["ids"]))
+    assert g["gaps"][first] <= 0.08, f"ids diverge from the golden ids at step {first} with a decisive top-2 gap {g['gaps'][first]:.4f}"
+    assert not np.array_equal(logits[:4], g["logits"]), "identical logits but different ids"
 
 
 @pytest.mark.parametrize("name", TINY)

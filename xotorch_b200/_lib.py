@@ -51,6 +51,7 @@ _SIGS = {
   "xotb200_select_request": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
   "xotb200_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+  "xotb200_forward_hop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p]),
   "xotb200_last_token": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
   "xotb200_inbox_export": (C.c_int, [C.c_void_p, C.c_void_p]),
   "xotb200_link_next_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -58,6 +59,7 @@ _SIGS = {
   "xotb200_post_to_next": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_ring_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
   "xotb200_ring_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+  "xotb200_ring_next_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
   "xotb200_ring_timestamps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
   "xotb200_set_cta_limit": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_set_prefill_mode": (C.c_int, [C.c_void_p, C.c_int]),

@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -129,10 +130,19 @@ struct xotb200_engine {
   float* cta_best_val = nullptr;
   int* cta_best_idx = nullptr;
   int nsplit = 1, nsplit_min = 1;
+  int attn_direct_max = 1024;      // see AttnPlan in megakernel_impl.inc (XOTB200_ATTN_DIRECT_MAX: tuning hook, 0 = always split)
   StepCtl* ctl = nullptr;
   InboxHdr* inbox = nullptr;
   InboxHdr* next_inbox = nullptr;
   bool next_ipc = false;
+  // API hop (xotb200_forward_hop): one engine call per shard per token with the hidden state moved by the producing kernel
+  xotb200_engine* next_engine = nullptr;   // same-process link: needed for multi-token (prompt) hops, which are peer copies
+  unsigned int hop_seq_next = 0;           // sender side: next hop number of this link (reset when the link is made)
+  std::mutex hop_mu;                       // receiver side: guards the growth of hop_buf
+  bf16* hop_buf[API_SLOTS] = {};           // receiver side: [n_tokens, D] prompt hidden states pushed by the previous engine
+  int hop_cap[API_SLOTS] = {};
+  int hop_in = 0, hop_out = 0;             // per-launch arguments of the API hop (see MegaArgs)
+  unsigned int hop_seq_in = 0, hop_seq_out = 0;
   int* tokens_log = nullptr;
   int* route_log = nullptr;         // sparse MoE: experts chosen per (position, local layer) of request 0
   unsigned long long *t_in = nullptr, *t_out = nullptr;
@@ -166,6 +176,7 @@ struct xotb200_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   int last_ring_steps = 0;
+  int ring_next_step = 0;          // first ring step number no run on this engine has used (inbox flags are never reused)
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -257,6 +268,7 @@ static int prepare_mega(xotb200_engine* e) {
   if (const char* v = getenv("XOTB200_NSPLIT")) e->nsplit = std::max(1, std::min(e->nsplit, atoi(v)));   // tuning hooks
   if (const char* v = getenv("XOTB200_NSPLIT_MIN")) e->nsplit_min = std::max(1, atoi(v));
   e->nsplit_min = std::min(e->nsplit_min, e->nsplit);
+  if (const char* v = getenv("XOTB200_ATTN_DIRECT_MAX")) e->attn_direct_max = std::max(0, atoi(v));
   return 0;
 }
 
@@ -274,11 +286,14 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.x = e->x; a.q = e->q; a.attn_out = e->attn_out; a.act = e->act; a.logits = e->logits;
   a.part_ml = e->part_ml; a.part_acc = e->part_acc; a.tickets = e->tickets;
   a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit; a.nsplit_min = e->nsplit_min;
+  a.attn_direct_max = e->attn_direct_max;
   a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
   a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
   a.nreq = e->nreq; a.nslots = e->nreq + 1; a.req0 = e->cur_req; a.kv_req_stride = e->kv_req_stride;
   a.src_tokens = e->stage_tokens; a.src_hidden = e->stage_in; a.out_hidden = e->stage_out;
+  a.hop_in = mode == 1 ? e->hop_in : 0; a.hop_out = mode == 1 ? e->hop_out : 0;
+  a.hop_seq_in = e->hop_seq_in; a.hop_seq_out = e->hop_seq_out;
   a.xbuf_bytes = e->mega_xbuf;
   a.E = c.n_experts; a.topk = c.experts_per_tok;
   a.gu_stride = (size_t)2 * c.ffn * c.dim; a.dn_stride = (size_t)c.dim * c.ffn;
@@ -354,6 +369,20 @@ static TcCfg tc_cfg(int N, int S) {
 }
 static int tc_nt(int N) { return tc_cfg(N, 1).nt; }
 
+// cudaFuncSetAttribute(max dynamic smem) once per (device, kernel).  The cache is process-wide and engines on different GPUs
+// run on different host threads (ctypes drops the GIL), so it is guarded by a mutex.
+static int ensure_smem_attr(int device, const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, bool> done;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(device, fn);
+  if (!done.count(key)) {
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done[key] = true;
+  }
+  return 0;
+}
+
 template <int NT, int NS>
 static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi,
                              cudaStream_t st) {
@@ -364,12 +393,7 @@ static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CU
     case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_RESID, NS> : xb::bf::tc_gemm_kernel<NT, TCE_RESID, NS>; break;
     default: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_HEAD_LAST, NS> : xb::bf::tc_gemm_kernel<NT, TCE_HEAD_LAST, NS>; break;
   }
-  static std::map<std::pair<int, void*>, bool> attr_done;
-  auto key = std::make_pair(e->device, (void*)fn);
-  if (!attr_done.count(key)) {
-    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT, NS)));
-    attr_done[key] = true;
-  }
+  if (int rc = ensure_smem_attr(e->device, (const void*)fn, tc_smem_bytes(NT, NS))) return rc;
   const int mtiles = a.grid_m > 0 ? a.grid_m : (epi == TCE_HEAD_LAST ? 1 : (a.S + TC_M - 1) / TC_M - a.mt0);
   fn<<<dim3(mtiles, a.N / NT), TC_THREADS, tc_smem_bytes(NT, NS), st>>>(tmA, tmB, a);
   CK(cudaGetLastError());
@@ -387,12 +411,7 @@ static int launch_tc_gemm_persistent(xotb200_engine* e, const CUtensorMap& tmA, 
     case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_RESID, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_RESID, NS>; break;
     default: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_HEAD_LAST, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_HEAD_LAST, NS>; break;
   }
-  static std::map<std::pair<int, void*>, bool> attr_done;
-  auto key = std::make_pair(e->device, (void*)fn);
-  if (!attr_done.count(key)) {
-    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(NT, NS)));
-    attr_done[key] = true;
-  }
+  if (int rc = ensure_smem_attr(e->device, (const void*)fn, tc_smem_bytes(NT, NS))) return rc;
   fn<<<std::min(tiles, e->sm_count), TC_THREADS, tc_smem_bytes(NT, NS), st>>>(tmA, tmB, a);
   CK(cudaGetLastError());
   e->launches++;
@@ -510,12 +529,7 @@ static int launch_tc_attn(xotb200_engine* e, int S, int R, bf16* kc, bf16* vc, i
   constexpr int SMEM = (64 + 4 * 64) * HD * 2;          // Q tile + 2 x (K, V) tiles
   const bool f16 = e->cfg.dtype == XOTB200_DTYPE_F16;
   auto fn = f16 ? xb::fp::tc_flash_attn_kernel<HD> : xb::bf::tc_flash_attn_kernel<HD>;
-  static std::map<std::pair<int, void*>, bool> attr_done;
-  auto key = std::make_pair(e->device, (void*)fn);
-  if (!attr_done.count(key)) {
-    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done[key] = true;
-  }
+  if (int rc = ensure_smem_attr(e->device, (const void*)fn, SMEM)) return rc;
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   fn<<<dim3((S + 63) / 64, e->cfg.n_heads), 128, SMEM, st>>>(e->tc_q, kc, vc, e->tc_ao, S, e->cfg.n_heads, R, e->L, pos0, scale_log2);
   CK(cudaGetLastError());
@@ -772,7 +786,7 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   CK(cudaMalloc(&e->bar_counter, 4));
   CK(cudaMalloc(&e->ctl, sizeof(StepCtl)));
   MEMSET_SYNC(e, e->ctl, 0, sizeof(StepCtl));
-  const size_t inbox_bytes = sizeof(InboxHdr) + (size_t)INBOX_SLOTS * D * 2;
+  const size_t inbox_bytes = sizeof(InboxHdr) + (size_t)(INBOX_SLOTS + API_SLOTS) * D * 2;
   CK(cudaMalloc(&e->inbox, inbox_bytes));
   MEMSET_SYNC(e, e->inbox, 0, inbox_bytes);
   CK(cudaMalloc(&e->tokens_log, MAX_RING_STEPS * 4));
@@ -793,6 +807,8 @@ int xotb200_destroy(xotb200_engine* e) {
   void* tcp[] = {e->tc_x, e->tc_xn, e->tc_qkv, e->tc_q, e->tc_ao, e->tc_gu, e->tc_act, e->moe_xg, e->moe_gu, e->moe_act, e->moe_y,
                  e->moe_route_e, e->moe_route_w, e->moe_row_of, e->moe_row_token, e->moe_exp_info};
   for (void* p : tcp)
+    if (p) cudaFree(p);
+  for (bf16* p : e->hop_buf)
     if (p) cudaFree(p);
   void* ptrs[] = {e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
                   e->cta_best_idx, e->ctl, e->bar_counter, e->dbg, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
@@ -933,7 +949,7 @@ int xotb200_load_shard(xotb200_engine* e, const char* dir, int start_layer, int 
     int fd = open(f.c_str(), O_RDONLY);
     if (fd < 0) { set_err("cannot open %s", f.c_str()); return XOTB200_EIO; }
     struct stat sb;
-    fstat(fd, &sb);
+    if (fstat(fd, &sb) != 0 || sb.st_size < 8) { close(fd); set_err("cannot stat %s (or shorter than a safetensors header)", f.c_str()); return XOTB200_EIO; }
     void* m = mmap(nullptr, sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (m == MAP_FAILED) { set_err("mmap failed for %s", f.c_str()); return XOTB200_EIO; }
@@ -942,17 +958,36 @@ int xotb200_load_shard(xotb200_engine* e, const char* dir, int start_layer, int 
     memcpy(&hlen, base, 8);
     std::map<std::string, StEntry> hdr;
     int rc = 0;
-    if (hlen + 8 > (uint64_t)sb.st_size || !parse_st_header(base + 8, hlen, hdr)) {
+    if (hlen > (uint64_t)sb.st_size - 8 || !parse_st_header(base + 8, hlen, hdr)) {
       set_err("bad safetensors header in %s", f.c_str());
       rc = XOTB200_EIO;
     }
+    const uint64_t data_bytes = (uint64_t)sb.st_size - 8 - hlen;
     for (auto it = hdr.begin(); rc == 0 && it != hdr.end(); ++it) {
       auto sl = e->slots.find(it->first);
-      if (sl == e->slots.end()) continue;
+      if (sl == e->slots.end()) {
+        // strict: a tensor of a layer this shard OWNS that has no slot (e.g. q_proj.bias of a biased-attention
+        // checkpoint) would be silently ignored and give wrong logits -> refuse the checkpoint
+        int l = -1;
+        if (sscanf(it->first.c_str(), "model.layers.%d.", &l) == 1 && l >= e->start && l <= e->end &&
+            it->first.find("rotary_emb.inv_freq") == std::string::npos) {
+          set_err("strict loader: tensor '%s' belongs to layer %d of this shard but the engine has no use for it (unsupported architecture variant)",
+                  it->first.c_str(), l);
+          rc = XOTB200_ESTRICT;
+        }
+        continue;
+      }
       const StEntry& en = it->second;
       const char* want = e->cfg.dtype == XOTB200_DTYPE_F16 ? "F16" : "BF16";
       if (en.dtype != want) { set_err("tensor %s: dtype %s but the engine was created for %s", it->first.c_str(), en.dtype.c_str(), want); rc = XOTB200_EIO; break; }
-      if ((uint64_t)(8 + hlen + en.end) > (uint64_t)sb.st_size) { set_err("tensor %s: data out of file bounds", it->first.c_str()); rc = XOTB200_EIO; break; }
+      uint64_t elems = 1;
+      bool shape_ok = !en.shape.empty() && en.shape.size() <= 2;
+      for (int64_t d : en.shape) { if (d <= 0 || d > (int64_t)1 << 40) shape_ok = false; else elems *= (uint64_t)d; }
+      if (!shape_ok || en.begin < 0 || en.end < en.begin || (uint64_t)en.end > data_bytes || (uint64_t)(en.end - en.begin) != elems * 2) {
+        set_err("tensor %s: data_offsets [%lld, %lld) do not match its shape / the file size", it->first.c_str(), (long long)en.begin, (long long)en.end);
+        rc = XOTB200_EIO;
+        break;
+      }
       rc = xotb200_load_tensor(e, it->first.c_str(), base + 8 + hlen + en.begin, en.shape.data(), (int)en.shape.size());
       if (rc == 1) rc = 0;
     }
@@ -1157,6 +1192,83 @@ int xotb200_forward_device(xotb200_engine* e, const int32_t* tokens, const void*
   return 0;
 }
 
+// ---- the API hop: one engine call per shard per token like xotb200_forward, but the hidden state never visits the host.
+//      decode (n_tokens == 1): the producing kernel's last epilogue stores it into the NEXT engine's inbox (peer store over
+//      NVLink + release flag, the ring-mode hop); the call returns WITHOUT synchronising — the next engine's kernel acquires the
+//      flag on the device, so it may be launched before this one has finished.
+//      prompts (n_tokens > 1): one peer copy of the 16-bit [n_tokens, D] block into the next engine's receive buffer
+//      (same-process links only; across processes use xotb200_forward_device + the caller's transport).
+int xotb200_forward_hop(xotb200_engine* e, const int32_t* tokens, int64_t seq_in, int n_tokens, int pos0, int64_t* seq_out,
+                        float* logits_f32) {
+  REQUIRE(e && e->start >= 0, "no shard set");
+  REQUIRE((tokens != nullptr) == e->first, "%s shard expects %s", e->first ? "first" : "non-first", e->first ? "token ids" : "a hop number");
+  REQUIRE(e->first || seq_in >= 0, "seq_in must name the hop to consume");
+  REQUIRE(n_tokens >= 1 && pos0 >= 0, "bad n_tokens/pos0");
+  REQUIRE(e->L > 0, "begin_request was not called");
+  REQUIRE(pos0 + n_tokens <= e->L, "KV cache overflow: pos0 %d + n %d > capacity %d", pos0, n_tokens, e->L);
+  REQUIRE(e->last ? (logits_f32 != nullptr) : (seq_out != nullptr && e->next_inbox != nullptr), e->last ? "null output" : "next engine not linked");
+  if (int rc = xotb200_check_loaded(e)) return rc;
+  CK(cudaSetDevice(e->device));
+  if (int rc = ensure_staging(e, n_tokens)) return rc;
+  const size_t D = e->cfg.dim;
+  cudaStream_t st = e->stream;
+  {   // an error left behind by an earlier asynchronous hop (flag wait timed out) surfaces here
+    StepCtl h;
+    CK(cudaMemcpyAsync(&h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h.err) {
+      MEMSET_SYNC(e, &e->ctl->err, 0, 4);
+      set_err("an earlier hop on this engine timed out waiting for the previous shard's flag");
+      return XOTB200_ETIMEOUT;
+    }
+  }
+  const bool decode = n_tokens == 1;
+  if (tokens) {
+    for (int i = 0; i < n_tokens; ++i)
+      REQUIRE(tokens[i] >= 0 && tokens[i] < e->cfg.vocab, "token id %d out of range", tokens[i]);
+    CK(cudaMemcpyAsync(e->stage_tokens, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st));
+  } else if (!decode) {
+    const int slot = (int)(seq_in % API_SLOTS);
+    REQUIRE(e->hop_buf[slot] && e->hop_cap[slot] >= n_tokens, "hop %lld: no prompt block of %d tokens was pushed into this engine", (long long)seq_in, n_tokens);
+    CK(cudaMemcpyAsync(e->stage_in, e->hop_buf[slot], (size_t)n_tokens * D * 2, cudaMemcpyDeviceToDevice, st));
+  }
+  unsigned int seq = 0;
+  if (!e->last) seq = e->hop_seq_next++;
+  e->hop_in = (!e->first && decode) ? 1 : 0;
+  e->hop_out = (!e->last && decode) ? 1 : 0;
+  e->hop_seq_in = (unsigned int)seq_in;
+  e->hop_seq_out = seq;
+  const bool use_tc = e->prefill_mode == 2 || (e->prefill_mode == 0 && n_tokens >= 8);
+  int rc = use_tc ? prefill_tc(e, n_tokens, pos0, st) : launch_mega(e, 1, n_tokens, 0, pos0, st);
+  e->hop_in = e->hop_out = 0;
+  if (rc) return rc;
+  if (e->last) {
+    CK(cudaMemcpyAsync(logits_f32, e->logits, (size_t)e->cfg.vocab * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  } else {
+    if (!decode) {
+      xotb200_engine* nx = e->next_engine;
+      REQUIRE(nx != nullptr, "multi-token hops need a same-process link (xotb200_link_next_local); across processes use xotb200_forward_device");
+      const int slot = (int)(seq % API_SLOTS);
+      {
+        std::lock_guard<std::mutex> lock(nx->hop_mu);
+        if (nx->hop_cap[slot] < n_tokens) {
+          CK(cudaSetDevice(nx->device));
+          if (nx->hop_buf[slot]) { CK(cudaFree(nx->hop_buf[slot])); nx->hop_buf[slot] = nullptr; nx->hop_cap[slot] = 0; }
+          CK(cudaMalloc(&nx->hop_buf[slot], (size_t)n_tokens * D * 2));
+          nx->hop_cap[slot] = n_tokens;
+          CK(cudaSetDevice(e->device));
+        }
+      }
+      CK(cudaMemcpyPeerAsync(nx->hop_buf[slot], nx->device, e->stage_out, e->device, (size_t)n_tokens * D * 2, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    *seq_out = (int64_t)seq;
+  }
+  e->have_result = true;
+  return 0;
+}
+
 int xotb200_last_token(xotb200_engine* e, int32_t* token) {
   REQUIRE(e && token, "null argument");
   REQUIRE(e->last && e->have_result, "no last-shard result available");
@@ -1181,6 +1293,14 @@ static void drop_next(xotb200_engine* e) {
   if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
   e->next_inbox = nullptr;
   e->next_ipc = false;
+  e->next_engine = nullptr;
+}
+// A new link starts its API-hop numbering at 0 and clears the receiver's API flags (they hold seq + 1 of the previous link).
+static int reset_hop_link(xotb200_engine* e) {
+  e->hop_seq_next = 0;
+  CK(cudaMemsetAsync(e->next_inbox->flag_api, 0, sizeof(e->next_inbox->flag_api), e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
 }
 
 int xotb200_link_next_ipc(xotb200_engine* e, const void* handle) {
@@ -1193,7 +1313,7 @@ int xotb200_link_next_ipc(xotb200_engine* e, const void* handle) {
   CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   e->next_inbox = static_cast<InboxHdr*>(p);
   e->next_ipc = true;
-  return 0;
+  return reset_hop_link(e);
 }
 
 int xotb200_link_next_local(xotb200_engine* e, xotb200_engine* next) {
@@ -1209,7 +1329,8 @@ int xotb200_link_next_local(xotb200_engine* e, xotb200_engine* next) {
     cudaGetLastError();
   }
   e->next_inbox = next->inbox;
-  return 0;
+  e->next_engine = next;
+  return reset_hop_link(e);
 }
 
 int xotb200_post_to_next(xotb200_engine* e, int step) {
@@ -1222,6 +1343,7 @@ int xotb200_post_to_next(xotb200_engine* e, int step) {
     post_kernel<<<1, 256, 0, e->stream>>>(e->next_inbox, e->x, e->cfg.dim, nullptr, step, e->nreq + 1);
   CK(cudaGetLastError());
   e->launches++;
+  e->ring_next_step = std::max(e->ring_next_step, step + 1);
   CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -1229,6 +1351,7 @@ int xotb200_post_to_next(xotb200_engine* e, int step) {
 int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0) {
   REQUIRE(e && e->start >= 0 && e->next_inbox, "ring not linked");
   REQUIRE(n_steps >= 1 && n_steps <= MAX_RING_STEPS, "n_steps out of range (1..%d)", MAX_RING_STEPS);
+  REQUIRE(step0 >= 0 && pos0 >= 0, "negative step0 / pos0");
   REQUIRE(n_steps % e->nreq == 0, "n_steps %d must be a multiple of the %d requests in flight", n_steps, e->nreq);
   REQUIRE(e->L > 0 && pos0 + n_steps / e->nreq <= e->L, "KV cache overflow: pos0 %d + %d steps per request > capacity %d", pos0,
           n_steps / e->nreq, e->L);
@@ -1239,6 +1362,7 @@ int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0) {
   if (int rc = launch_mega(e, 0, n_steps, step0, pos0, st)) return rc;
   CK(cudaEventRecord(e->ev1, st));
   e->last_ring_steps = n_steps;
+  e->ring_next_step = std::max(e->ring_next_step, step0 + n_steps);
   return 0;
 }
 
@@ -1260,6 +1384,12 @@ int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float
   }
   if (ms_out) CK(cudaEventElapsedTime(ms_out, e->ev0, e->ev1));
   e->have_result = true;
+  return 0;
+}
+
+int xotb200_ring_next_step(xotb200_engine* e, int* step) {
+  REQUIRE(e && step, "null argument");
+  *step = e->ring_next_step;
   return 0;
 }
 
@@ -1290,6 +1420,10 @@ int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16
   REQUIRE(S >= 1 && S <= TC_M && K % tk == 0 && tk % TC_BK == 0 && N % tc_nt(N) == 0, "bad GEMM shape S=%d N=%d K=%d tk=%d", S, N, K, tk);
   CK(cudaSetDevice(e->device));
   bf16 *dA = nullptr, *dW0 = nullptr, *dW = nullptr, *dO = nullptr;
+  struct Free4 {   // every exit path (CK returns early) releases the four scratch allocations
+    bf16 **a, **b, **c, **d;
+    ~Free4() { for (bf16** p : {a, b, c, d}) if (*p) cudaFree(*p); }
+  } guard{&dA, &dW0, &dW, &dO};
   CK(cudaMalloc(&dA, (size_t)TC_M * K * 2));
   CK(cudaMalloc(&dW0, (size_t)N * K * 2));
   CK(cudaMalloc(&dW, (size_t)N * K * 2));
@@ -1311,7 +1445,6 @@ int xotb200_debug_gemm(xotb200_engine* e, const void* a_bf16, const void* w_bf16
     er = cudaMemcpyAsync(out_bf16, dO, (size_t)S * N * 2, cudaMemcpyDeviceToHost, e->stream);
     if (er == cudaSuccess) er = cudaStreamSynchronize(e->stream);
   }
-  cudaFree(dA); cudaFree(dW0); cudaFree(dW); cudaFree(dO);
   if (rc) return rc;
   CK(er);
   return 0;

@@ -25,14 +25,16 @@ struct StepCtl {
 };
 
 // Inbox: lives in the RECEIVER's HBM; written by the previous shard over NVLink (or locally for a 1-shard ring).
-constexpr int INBOX_SLOTS = 9;   // up to 8 requests in flight through a ring + 1
+constexpr int INBOX_SLOTS = 9;   // ring mode: up to 8 requests in flight through a ring + 1
+constexpr int API_SLOTS = 8;     // API hop (xotb200_forward_hop, one engine call per shard per token): hops in flight per link
 struct InboxHdr {
   unsigned int flag_hidden[INBOX_SLOTS];   // == step+1 when hidden[slot] holds the activation of ring step `step`
   unsigned int flag_token[INBOX_SLOTS];    // == step+1 when token[slot] holds the token id feeding ring step `step`
   int token[INBOX_SLOTS];
-  int pad[32 - 3 * INBOX_SLOTS];           // header is 128 bytes; bf16 hidden[INBOX_SLOTS][D] follows
+  unsigned int flag_api[API_SLOTS];        // == seq+1 when hidden[INBOX_SLOTS + seq % API_SLOTS] holds API hop `seq` of this link
+  int pad[64 - 3 * INBOX_SLOTS - API_SLOTS];   // header is 256 bytes; bf16 hidden[INBOX_SLOTS + API_SLOTS][D] follows
 };
-static_assert(sizeof(InboxHdr) == 128, "InboxHdr must be 128 bytes");
+static_assert(sizeof(InboxHdr) == 256, "InboxHdr must be 256 bytes");
 
 // ------------------------------------------------------------------------------------------------------------
 // PTX helpers

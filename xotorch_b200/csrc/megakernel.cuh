@@ -67,12 +67,17 @@ struct MegaArgs {
   float* cta_best_val;
   int* cta_best_idx;
   int nsplit, nsplit_min;   // context splits per kv head: upper bound (CTAs / kv heads) and the count used for short contexts
+  int attn_direct_max;      // contexts up to this length: one CTA per QUERY head does the whole attention (no split partials / ticket)
   StepCtl* ctl;
   InboxHdr *inbox, *next_inbox;
   int* tokens_log;
   unsigned long long *t_in, *t_out;
   unsigned int* bar_counter; // grid barrier counter (host zeroes it before every launch)
   int mode;                  // 0 ring, 1 direct
+  // direct mode, one step (the API hop, xotb200_forward_hop): the hidden state arrives in / leaves through the inbox's API slots
+  // — the same fused peer store + release/acquire flag as ring mode, but one engine call per shard per token
+  int hop_in, hop_out;       // 1: input from this engine's inbox API slot / output into the next engine's
+  unsigned int hop_seq_in, hop_seq_out;   // hop sequence numbers (slot = seq % API_SLOTS, flag value = seq + 1)
   int n_steps, step0, pos0;
   int nreq;                  // requests in flight (ring mode): ring step s serves request s % nreq at position pos0 + s / nreq
   int nslots;                // inbox slots in use = nreq + 1 (a shard is never more than nreq-1 steps ahead of the next one)

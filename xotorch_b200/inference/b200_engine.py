@@ -29,6 +29,22 @@ TEMP = 0.6      # sharded_inference_engine.py:34
 TOP_K = 35      # sharded_inference_engine.py:35
 MAX_GENERATED_TOKENS = 1024   # general_mha.py:152: KV length = prompt + 1024
 
+# Device-resident hop (xotb200_forward_hop): when the next shard's engine lives in this process (NVLinkPeerHandle), the
+# "tensor" a non-last shard returns — and PeerHandle.send_tensor carries — is this 4-word descriptor instead of the fp32
+# hidden state; the payload was stored into the next engine's HBM by the producing kernel (SURVEY.md §8b "Hop API").
+HOP_MAGIC = 0x584F5442   # "XOTB"
+
+
+def make_hop_descriptor(seq: int, n_tokens: int, dim: int) -> np.ndarray:
+  return np.array([[[HOP_MAGIC, int(seq), int(n_tokens), int(dim)]]], dtype=np.int64)
+
+
+def parse_hop_descriptor(x: np.ndarray):
+  """(seq, n_tokens, dim) if `x` is a hop descriptor, else None.  ndim 3 like a hidden state, but int64 [1, 1, 4] + magic."""
+  if isinstance(x, np.ndarray) and x.dtype == np.int64 and x.shape == (1, 1, 4) and int(x[0, 0, 0]) == HOP_MAGIC:
+    return int(x[0, 0, 1]), int(x[0, 0, 2]), int(x[0, 0, 3])
+  return None
+
 
 def reference_sample(logits: np.ndarray, temp: float, top_k: int, q: np.ndarray) -> np.ndarray:
   """torchtune.generation.sample restated on host arrays: /max(temp,1e-5), top-k mask,
@@ -90,6 +106,9 @@ class B200ShardInferenceEngine(InferenceEngine):
     self.max_concurrent_requests = int(max_concurrent_requests)
     self.max_total_len = max_total_len
     self._slots: Dict[str, int] = {}                        # request_id -> KV slot, in least-recently-used order
+    self._hop_next: Optional["B200ShardInferenceEngine"] = None   # engine of the next shard when it lives in this process
+    self._hop_linked = None                                 # (own native, its native) the device link was made for
+    self.hop_stats = {"device_out": 0, "device_in": 0, "host_out": 0, "host_in": 0}
     import torch
     self._rng = torch.Generator(device="cpu")
     self._rng.manual_seed(1234)                             # sharded_inference_engine.py:67-69
@@ -103,6 +122,24 @@ class B200ShardInferenceEngine(InferenceEngine):
       return self._native_factory(hf_config, self.device)
     from xotorch_b200.native import NativeShard             # raises ImportError if libxotb200.so is missing
     return NativeShard(hf_config, self.device)
+
+  # ---- device-resident hop ---------------------------------------------------------------------------------------
+  def attach_next_engine(self, nxt: Optional["B200ShardInferenceEngine"]) -> None:
+    """Called by NVLinkPeerHandle.connect(): the engine that runs the NEXT shard of the ring lives in this process (another GPU
+    of the box, or this one).  From then on a non-last shard hands its hidden state over on the device."""
+    self._hop_next = nxt
+    self._hop_linked = None
+
+  def _hop_ready(self) -> bool:
+    """Link this engine's native object to the next engine's (lazily: both load their shard on first use, and a changed
+    shard means a new native object).  Runs on this engine's executor thread."""
+    nxt = self._hop_next
+    if nxt is None or self.native is None or nxt.native is None or not hasattr(self.native, "forward_hop"):
+      return False
+    if self._hop_linked != (id(self.native), id(nxt.native)):
+      self.native.link_next_local(nxt.native)               # enables peer access, clears the link's flags
+      self._hop_linked = (id(self.native), id(nxt.native))
+    return True
 
   # ---- reference API ---------------------------------------------------------------------------------------------
   async def ensure_shard(self, shard: Shard):
@@ -157,16 +194,43 @@ class B200ShardInferenceEngine(InferenceEngine):
     if input_data.ndim not in (2, 3):
       raise ValueError(f"input_data.ndim must be 2 (token ids) or 3 (hidden state), got {input_data.ndim}")
     start_pos = int(inference_state["curr_pos"]) if inference_state and "curr_pos" in inference_state else 0
-    n = input_data.shape[1]
+    hop_in = parse_hop_descriptor(input_data)               # the previous shard already put the hidden state into our HBM
+    if hop_in is not None and hop_in[2] != self.model_config["hidden_size"]:
+      raise ValueError(f"hop descriptor for hidden size {hop_in[2]} reached a model of hidden size {self.model_config['hidden_size']}")
+    n = hop_in[1] if hop_in is not None else input_data.shape[1]
     self.request_id = request_id
 
+    def run_native(pos):
+      """one step on the native engine; device-resident hop where the link allows it, host arrays otherwise"""
+      last = shard.is_last_layer()
+      host_hidden_in = hop_in is None and input_data.ndim == 3
+      send_dev = (not last) and (not host_hidden_in) and self._hop_ready()
+      if hop_in is None and not send_dev:                   # classic step on host arrays (xotb200_forward)
+        self.hop_stats["host_in"] += 1 if host_hidden_in else 0
+        self.hop_stats["host_out"] += 0 if last else 1
+        return self.native.forward(input_data, pos)
+      if not last and not send_dev:
+        raise RuntimeError("received a device-hop descriptor but the next shard's engine is not attached to this one")
+      seq_out, logits = self.native.forward_hop(input_data if hop_in is None else None, -1 if hop_in is None else hop_in[0], n, pos)
+      if hop_in is not None:
+        self.hop_stats["device_in"] += 1
+      if last:
+        return logits
+      self.hop_stats["device_out"] += 1
+      return make_hop_descriptor(seq_out, n, self.model_config["hidden_size"])
+
     def step():
-      need = max(n + MAX_GENERATED_TOKENS, int((inference_state or {}).get("max_total_len", 0)))
+      # KV capacity = prompt + 1024 like the reference (general_mha.py:152), clamped to the model's context: a prompt that fits
+      # the context must not be refused because prompt + 1024 does not
+      max_pos = int(self.model_config["max_position_embeddings"])
+      if start_pos + n > max_pos:
+        raise RuntimeError(f"{start_pos + n} positions exceed the model's context of {max_pos} (max_position_embeddings)")
+      need = min(max(n + MAX_GENERATED_TOKENS, int((inference_state or {}).get("max_total_len", 0))), max_pos)
       if self.max_concurrent_requests <= 1:
         if start_pos == 0:
           self.native.begin_request(need)
           self._kv_capacity = need
-        return self.native.forward(input_data, start_pos)
+        return run_native(start_pos)
       # several requests in flight: one KV slot per request id (xotb200_begin_batch / xotb200_select_request)
       if start_pos == 0:
         if self._kv_capacity == 0:
@@ -187,10 +251,10 @@ class B200ShardInferenceEngine(InferenceEngine):
       if start_pos + n > self._kv_capacity:
         raise RuntimeError(f"request {request_id!r} reached the KV capacity {self._kv_capacity}")
       self.native.select_request(slot)
-      return self.native.forward(input_data, start_pos)
+      return run_native(start_pos)
     out = await self._run(step)
     if shard.is_last_layer():
-      new_pos = n if start_pos == 0 else start_pos + 1
+      new_pos = start_pos + n          # the reference advances by 1 per decode step (:356-359); n > 1 continuation chunks advance by n
     else:
       new_pos = start_pos
     self._pos = new_pos

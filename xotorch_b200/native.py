@@ -25,6 +25,22 @@ def cfg_from_hf(hf: dict) -> ModelCfg:
   else:
     raise ValueError(f"torch_dtype {dt!r}: libxotb200 implements 16-bit weights (bfloat16, float16) with fp32 accumulation")
   rs = hf.get("rope_scaling")
+  # Only what the kernels implement is accepted; anything else would load without error and give wrong logits
+  # (the reference builds biased attention for Qwen2, general_mha.py:45-53; other RoPE scalings exist upstream in HF).
+  if rs is not None:
+    kind = rs.get("rope_type", rs.get("type"))
+    if kind != "llama3":
+      raise ValueError(f"rope_scaling type {kind!r}: libxotb200 implements plain RoPE and the 'llama3' scaling only")
+  for key in ("attention_bias", "mlp_bias"):
+    if hf.get(key):
+      raise ValueError(f"{key}=true: biased projections are not implemented by libxotb200")
+  if hf.get("hidden_act", "silu") != "silu":
+    raise ValueError(f"hidden_act {hf.get('hidden_act')!r}: only SwiGLU (silu) MLPs are implemented")
+  if hf.get("sliding_window") not in (None, 0):
+    raise ValueError("sliding_window attention is not implemented by libxotb200")
+  mt = hf.get("model_type")
+  if mt not in (None, "llama", "mixtral", "mistral"):
+    raise ValueError(f"model_type {mt!r}: libxotb200 implements Llama-style dense and Mixtral-style sparse-MoE decoders")
   c = ModelCfg()
   c.n_layers = hf["num_hidden_layers"]
   c.dim = hf["hidden_size"]
@@ -146,6 +162,20 @@ class NativeShard:
                                           logits.ctypes.data_as(C.c_void_p) if logits is not None else None))
     return logits
 
+  def forward_hop(self, ids: Optional[np.ndarray], seq_in: int, n_tokens: int, pos0: int) -> Tuple[Optional[int], Optional[np.ndarray]]:
+    """One step with the hidden state handed over on the device (xotb200_forward_hop): first shard passes `ids` [1, S], other
+    shards the hop number `seq_in` their predecessor returned.  Returns (hop number produced | None, logits [1, V] | None).
+    For S == 1 a non-last shard returns without waiting for its kernel: the next shard's kernel acquires the flag itself."""
+    tok_p = None
+    if ids is not None:
+      ids = np.ascontiguousarray(ids, dtype=np.int32)
+      tok_p = ids.ctypes.data_as(C.c_void_p)
+    logits = np.empty((1, self.cfg.vocab), dtype=np.float32) if self.is_last else None
+    seq_out = C.c_int64(-1)
+    check(self.lib.xotb200_forward_hop(self.h, tok_p, C.c_int64(int(seq_in)), int(n_tokens), int(pos0), C.byref(seq_out),
+                                       logits.ctypes.data_as(C.c_void_p) if logits is not None else None))
+    return (None if self.is_last else int(seq_out.value)), logits
+
   def last_token(self) -> int:
     t = C.c_int32()
     check(self.lib.xotb200_last_token(self.h, C.byref(t)))
@@ -179,6 +209,12 @@ class NativeShard:
     else:
       check(self.lib.xotb200_ring_wait(self.h, None, 0, C.byref(ms)))
     return toks, float(ms.value)
+
+  def ring_next_step(self) -> int:
+    """first ring step number not yet used on this engine (inbox flags are monotonic and never cleared)"""
+    v = C.c_int()
+    check(self.lib.xotb200_ring_next_step(self.h, C.byref(v)))
+    return int(v.value)
 
   def ring_timestamps(self, n_steps: int) -> Tuple[np.ndarray, np.ndarray]:
     t_in = np.empty(n_steps, dtype=np.uint64)

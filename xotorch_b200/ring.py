@@ -27,7 +27,12 @@ class LocalRing:
         e.set_cta_limit(sms // n)           # persistent kernels sharing one GPU must be co-resident
     for i, e in enumerate(self.engines):
       e.link_next_local(self.engines[(i + 1) % n])
-    self._step = 0
+    self._sync_step()
+
+  def _sync_step(self):
+    """Ring step numbers are never reused on an engine (its inbox flags hold step+1 and are not cleared): a new ring over
+    existing engines, or a ring recovering from a timeout, continues after the highest number any of them has seen."""
+    self._step = max(e.ring_next_step() for e in self.engines)
 
   def prefill(self, prompt_ids: np.ndarray, max_total_len: int) -> np.ndarray:
     """host-buffer API through all shards; returns the last-position logits [1, V]."""
@@ -45,15 +50,19 @@ class LocalRing:
     first = self.engines[-1].last_token()
     if n_gen == 1:
       return np.array([first], dtype=np.int32), 0.0
-    self.engines[-1].post_to_next(self._step)
-    for e in self.engines:
-      e.ring_launch(n_gen - 1, self._step, s)
+    self._sync_step()
+    step0 = self._step
+    self.engines[-1].post_to_next(step0)
     toks, ms = None, 0.0
-    for e in self.engines:
-      t, m = e.ring_wait(n_gen - 1)
-      toks = t if t is not None else toks
-      ms = max(ms, m)
-    self._step += n_gen - 1
+    try:
+      for e in self.engines:
+        e.ring_launch(n_gen - 1, step0, s)
+      for e in self.engines:
+        t, m = e.ring_wait(n_gen - 1)
+        toks = t if t is not None else toks
+        ms = max(ms, m)
+    finally:
+      self._sync_step()                     # also after XOTB200_ETIMEOUT: the numbers of the failed run stay burnt
     return np.concatenate([[first], toks]).astype(np.int32), ms
 
   def generate_batch(self, prompts: np.ndarray, n_gen: int) -> Tuple[np.ndarray, float]:
@@ -61,6 +70,7 @@ class LocalRing:
     request s % B, so with B >= number of shards no GPU idles.  Returns (ids [B, n_gen], decode ms)."""
     prompts = np.asarray(prompts, dtype=np.int32)
     B, S = prompts.shape
+    self._sync_step()
     self._step = (self._step + B - 1) // B * B                 # ring step numbers of a batch start at a multiple of B
     for e in self.engines:
       e.begin_batch(S + n_gen + 1, B)
@@ -76,14 +86,16 @@ class LocalRing:
     if n_gen == 1:
       return np.array(first, dtype=np.int32).reshape(B, 1), 0.0
     n_steps = B * (n_gen - 1)
-    for e in self.engines:
-      e.ring_launch(n_steps, self._step, S)
     toks, ms = None, 0.0
-    for e in self.engines:
-      t, m = e.ring_wait(n_steps)
-      toks = t if t is not None else toks
-      ms = max(ms, m)
-    self._step += n_steps
+    try:
+      for e in self.engines:
+        e.ring_launch(n_steps, self._step, S)
+      for e in self.engines:
+        t, m = e.ring_wait(n_steps)
+        toks = t if t is not None else toks
+        ms = max(ms, m)
+    finally:
+      self._sync_step()
     ids = np.concatenate([np.array(first, dtype=np.int32).reshape(B, 1), toks.reshape(n_gen - 1, B).T], axis=1)
     return ids, ms
 
@@ -107,15 +119,19 @@ class DistributedRing:
     self.comm_device = comm_device
     self.first, self.last = native.is_first, native.is_last
     self.step = 0                      # monotonic ring step counter, identical on every rank
+    self.hops = 0                      # API hops made on every link since link() (identical on every rank)
 
   # -- link: every engine learns the inbox of the next one -----------------------------------------------------------
   def link(self):
     if self.world == 1:
       self.native.link_next_local(self.native)
+      self.step = self.native.ring_next_step()
       return
     handles = [None] * self.world
-    self.dist.all_gather_object(handles, self.native.inbox_export())
-    self.native.link_next_ipc(handles[self.next])
+    self.dist.all_gather_object(handles, (self.native.inbox_export(), self.native.ring_next_step()))
+    self.native.link_next_ipc(handles[self.next][0])      # also restarts the link's API-hop numbering at 0
+    self.hops = 0
+    self.step = max(h[1] for h in handles)      # never reuse a step number any engine of the ring has seen (flags are monotonic)
     self.dist.barrier()
 
   # -- host-array hop (API-compatible path) -----------------------------------------------------------------------------
@@ -195,26 +211,22 @@ class DistributedRing:
     return out
 
   def api_decode_device(self, first_token: int, pos0: int, n_gen: int) -> List[int]:
-    """`api_decode` with the hop kept on the GPUs: every rank still makes one engine call per token (token ids come from
-    host memory on the first shard, logits go back to host memory on the last — the user-visible API), but the hidden
-    state [1, D] travels rank to rank as a 16-bit device tensor (NCCL send/recv over NVLink, `xotb200_forward_device`)
-    instead of through fp32 host arrays."""
-    import torch
+    """`api_decode` with the hop kept on the GPUs — what NVLinkPeerHandle does behind PeerHandle.send_tensor: every rank still
+    makes ONE engine call per token (`xotb200_forward_hop`: token ids from host memory on the first shard, fp32 logits to host
+    memory on the last — the user-visible API), but the hidden state is stored into the next rank's inbox by the producing
+    kernel (peer store over NVLink + release flag through the CUDA-IPC mapping) and acquired there by the consuming kernel:
+    no NCCL send/recv, no stream synchronisation per hop.  Non-last ranks return from the call at once, so a rank's kernel for
+    token k is usually already waiting on its flag when the hidden state lands.  Only the 4-byte token id that closes the ring
+    travels through torch.distributed (the reference sends it to the first shard as a tensor too, node.py:119-147)."""
     if self.world == 1:
       return self.api_decode(first_token, pos0, n_gen)
-    dt = torch.float16 if self.native.cfg.dtype == 1 else torch.bfloat16
-    h = None if self.first else torch.empty((1, self.dim), dtype=dt, device=self.comm_device)
-    out = None if self.last else torch.empty((1, self.dim), dtype=dt, device=self.comm_device)
     tok, pos, ids_out = first_token, pos0, []
     for _ in range(n_gen):
-      if h is not None:
-        self.dist.recv(h, self.prev)
-        torch.cuda.current_stream().synchronize()
-      logits = self.native.forward_device(np.array([[tok]], dtype=np.int32) if self.first else None,
-                                          h.data_ptr() if h is not None else None, 1, pos,
-                                          out.data_ptr() if out is not None else None)
-      if out is not None:
-        self.dist.send(out, self.next)
+      # every link of the ring carries exactly one hop per token, so the number of the hop to consume is a local count
+      seq_out, logits = self.native.forward_hop(np.array([[tok]], dtype=np.int32) if self.first else None,
+                                                -1 if self.first else self.hops, 1, pos)
+      assert self.last or seq_out == self.hops, f"hop numbering out of step: produced {seq_out}, expected {self.hops}"
+      self.hops += 1
       if self.last:
         tok = int(np.argmax(logits[0]))
       tok = self._bcast_token(tok)              # ring closure: the id travels back to the first shard
@@ -231,9 +243,11 @@ class DistributedRing:
       self.native.post_to_next(s0)
     if self.world > 1:
       self.dist.barrier()
-    self.native.ring_launch(n_steps, s0, pos0)
-    toks, ms = self.native.ring_wait(n_steps)
-    self.step += n_steps
+    try:
+      self.native.ring_launch(n_steps, s0, pos0)
+      toks, ms = self.native.ring_wait(n_steps)
+    finally:
+      self.step = s0 + n_steps                # also on XOTB200_ETIMEOUT: the numbers of a failed run stay burnt
     return toks, ms
 
   # -- B requests in flight: ring step s serves request s % B; with B >= world no GPU idles ------------
@@ -259,9 +273,12 @@ class DistributedRing:
     if n_steps:
       if self.world > 1:
         self.dist.barrier()
-      self.native.ring_launch(n_steps, self.step, S)
-      toks, ms = self.native.ring_wait(n_steps)
-      self.step += n_steps
+      s0 = self.step
+      try:
+        self.native.ring_launch(n_steps, s0, S)
+        toks, ms = self.native.ring_wait(n_steps)
+      finally:
+        self.step = s0 + n_steps
     if not self.last:
       return None, ms
     ids = np.array(first, dtype=np.int32).reshape(B, 1)
