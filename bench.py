@@ -111,17 +111,17 @@ def usable_cores() -> int:
   return max(1, n)
 
 
-def even_partition(n_layers: int, n: int, rank: int):
-  """Ring partition for equal-memory GPUs == RingMemoryWeightedPartitioningStrategy + map_partitions_to_shards
-  (reference topology/*; xotorch_b200/topology/partitioning.py) on equal `memory`."""
-  from xotorch_b200.topology.partitioning import Partition, map_partitions_to_shards
-  parts, start = [], 0.0
-  for i in range(n):
-    end = round(start + 1.0 / n, 5)
-    parts.append(Partition(str(i), start, end))
-    start = end
-  shards = map_partitions_to_shards(parts, n_layers, MODEL)
-  return shards[rank].start_layer, shards[rank].end_layer
+def ring_partition(hf_cfg: dict, n: int, rank: int, how: str):
+  """Layer range of ring position `rank` on n equal-HBM GPUs.  "layers": the reference rule
+  (RingMemoryWeightedPartitioningStrategy + map_partitions_to_shards, topology/*).  "bytes": the same ring order with the
+  bytes each shard streams per token balanced (the last shard also streams the lm_head) — xotorch_b200/topology/partitioning.py."""
+  from xotorch_b200.topology.partitioning import (ByteBalancedRingPartitioningStrategy, RingMemoryWeightedPartitioningStrategy,
+                                                   map_partitions_to_shards)
+  mems = {f"gpu{n - 1 - i:02d}": 183359 for i in range(n)}          # ids chosen so that ring position i == rank i
+  st = ByteBalancedRingPartitioningStrategy.for_model(hf_cfg) if how == "bytes" else RingMemoryWeightedPartitioningStrategy()
+  shards = map_partitions_to_shards(st.partition(mems), hf_cfg["num_hidden_layers"], MODEL)
+  assert len(shards) == n
+  return shards[rank].start_layer, shards[rank].end_layer, [s.get_layer_count() for s in shards]
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -251,7 +251,7 @@ def run_b200(args):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
   shape = PRESETS[MODEL]
   cfg = hf_config(shape)
-  a, b = even_partition(shape.n_layers, n, rank) if n > 1 else (0, shape.n_layers - 1)
+  a, b, layer_counts = ring_partition(cfg, n, rank, args.partition) if n > 1 else (0, shape.n_layers - 1, [shape.n_layers])
   eng = NativeShard(cfg, device=local)
   eng.set_shard(a, b)
   eng.init_synthetic(SEED)
@@ -441,7 +441,10 @@ def run_b200(args):
       "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16" if shape.dtype == "float16" else "bf16", "data": "synthetic",
       "config": {"workload": workload_string(shape.dtype),
                  "step": "one request: prefill (untimed) + the timed decode of all generated tokens; weights generated on the device",
-                 "shards": n, "layers_per_shard": (b - a + 1), "partitioning": "ring, equal HBM",
+                 "shards": n, "layers_per_shard": layer_counts,
+                 "partitioning": ("ring order by (memory, id) like the reference, equal HBM; " +
+                                  ("bytes streamed per token balanced: the last shard also streams the lm_head (ByteBalancedRingPartitioningStrategy)"
+                                   if args.partition == "bytes" and n > 1 else "equal layer counts (the reference rule)")),
                  "l2_policy": f"inputs larger than L2 ({step_bytes_total / 1e9:.1f} GB of weights + KV streamed per token vs 126 MB L2)",
                  "prefill_ms_host_api": round(prefill_ms, 1),
                  "prefill_ms_device_hop": None if prefill_dev_ms is None else round(prefill_dev_ms, 1), "first_ids": first_ids,
@@ -474,6 +477,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--partition", default="bytes", choices=["bytes", "layers"], help="N>1: balance streamed bytes (default) or layer counts (reference rule)")
   ap.add_argument("--no-single-shard-check", action="store_true", help="N>1: skip re-running the request on ONE shard holding all layers")
   ap.add_argument("--no-ref-hop", action="store_true", help="--impl reference --gpus N>1: skip the reference gRPC hop comparator")
   # the other BASELINE.json configs through the same contract (defaults = the headline config):

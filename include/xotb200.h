@@ -76,7 +76,9 @@ int xotb200_destroy(xotb200_engine* e);
  *      Inclusive layer range as in Shard (xotorch/inference/shard.py:4-39).  Embedding is held only by the first
  *      shard, final norm + lm_head only by the last (App. B6).  The loader is STRICT (App. B6). ---- */
 int xotb200_set_shard(xotb200_engine* e, int start_layer, int end_layer);
-/* set_shard + read every *.safetensors in `dir` (HF names, HF layout; q/k re-laid out like _permute, llm_utils.py:175-183) */
+/* set_shard + read every *.safetensors in `dir` (HF names, HF layout; q/k re-laid out like _permute, llm_utils.py:175-183).
+ * Streams: file mapping -> pinned double buffer (parallel copy) -> DMA -> re-layout kernel, chunk i+1 overlapping chunk i; strict:
+ * missing tensors, unknown tensors of an owned layer, wrong dtype/shape and inconsistent data_offsets are errors. */
 int xotb200_load_shard(xotb200_engine* e, const char* safetensors_dir, int start_layer, int end_layer);
 /* one tensor by HF name from a host buffer (16-bit patterns in the engine's dtype); tensors outside the shard are ignored (returns 1) */
 int xotb200_load_tensor(xotb200_engine* e, const char* hf_name, const void* host_data, const int64_t* shape, int ndim);
@@ -145,6 +147,19 @@ int xotb200_post_to_next(xotb200_engine* e, int step);
 /* Launch the persistent kernel for n_steps ring steps starting at ring step `step0`, position `pos0`; asynchronous.
  * With a batch of B requests n_steps must be a multiple of B (n_steps / B tokens per request) and step0 a multiple of B. */
 int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0);
+/* Continuous batching: the same launch over an explicit set of n_active requests of the batch (xotb200_begin_batch), request i
+ * living in KV cache kv_slots[i] and standing at position positions[i]; ring step s serves active request s % n_active.  Requests
+ * join (prefill into a free slot with xotb200_select_request + xotb200_forward, then xotb200_post_token) and leave between
+ * launches — the per-slot position table the reference's Node keeps per request (node.py:119-147) moved next to the kernel. */
+int xotb200_ring_launch_slots(xotb200_engine* e, int n_steps, int step0, const int32_t* kv_slots, const int32_t* positions, int n_active);
+/* Last shard: seed ring step `step` of the first shard with an explicit token id (n_active = requests in flight in that run). */
+int xotb200_post_token(xotb200_engine* e, int step, int32_t token, int n_active);
+/* Last shard: tokens produced so far by the CURRENT ring launch, readable while its persistent kernel is still running (pinned
+ * mapped host memory written by the kernel).  Copies up to max_n ids starting at index `from`; *n_done = tokens produced so far.
+ * This is what a Node.on_token bridge streams from (the reference fires on_token once per token, node.py:127-137). */
+int xotb200_ring_poll(xotb200_engine* e, int32_t* tokens_out, int from, int max_n, int* n_done);
+/* Zero the KV cache of one request slot of the batch (reset_caches for ONE request, llm_utils.py:409-414). */
+int xotb200_clear_request(xotb200_engine* e, int request);
 /* Wait for the engine's stream; on the last shard copies the n_steps generated token ids (int32) to tokens_out
  * (may be NULL).  ms_out (may be NULL) = device time of the launched steps by CUDA events. */
 int xotb200_ring_wait(xotb200_engine* e, int32_t* tokens_out, int n_steps, float* ms_out);
@@ -177,6 +192,9 @@ int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, 
 
 /* ---- introspection ---- */
 int xotb200_kernel_launches(xotb200_engine* e, int64_t* count); /* kernels launched by this engine so far */
+/* the most recent xotb200_load_shard: bytes moved into HBM, wall seconds of the whole load, seconds of it spent copying out of
+ * the file mapping into the pinned staging buffers (the rest overlaps: DMA + re-layout kernels) */
+int xotb200_load_stats(xotb200_engine* e, int64_t* bytes, double* seconds, double* memcpy_seconds);
 int xotb200_weight_bytes(xotb200_engine* e, int64_t* bytes);    /* resident weight bytes of the current shard */
 int xotb200_step_bytes(xotb200_engine* e, int ctx, int64_t* bytes); /* algorithmic HBM bytes of one decode step at context ctx */
 

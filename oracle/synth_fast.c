@@ -2,8 +2,12 @@
  * baseline can materialise Llama-3-8B-shaped bf16 weights in seconds.  Bit-identical to the torch generator and to
  * the device generator (csrc/kernels.cuh::synth_value); checked in tests/test_oracle.py.
  * Build: gcc -O3 -fopenmp -shared -fPIC -o oracle/_build/libsynthfast.so oracle/synth_fast.c */
+#include <omp.h>
 #include <stdint.h>
 #include <string.h>
+
+/* The GPU box exposes every host core but runs the container under a CPU quota: size the team from the caller. */
+void synth_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 static inline uint16_t f32_to_bf16_rne(float f) {
   uint32_t u;

@@ -12,10 +12,36 @@ from .build import build, OUT
 _lib = None
 
 
+def usable_cores() -> int:
+  """Host cores this process may actually use: min(sched affinity, cgroup cpu quota).  The GPU box shows all 128 cores of the
+  host but runs the container under a quota of 16: a thread team sized by the affinity mask makes the CPU oracle crawl."""
+  import os
+  from pathlib import Path
+  n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+  for p in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+    try:
+      txt = Path(p).read_text().split()
+      if p.endswith("cpu.max"):
+        if txt[0] != "max":
+          n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+      else:
+        q = int(txt[0])
+        if q > 0:
+          per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+          n = min(n, max(1, int(q / per + 0.5)))
+      break
+    except Exception:
+      continue
+  return max(1, n)
+
+
 def _load():
   global _lib
   if _lib is None:
     lib = C.CDLL(str(build()))
+    lib.synth_set_threads.argtypes = [C.c_int]
+    lib.synth_set_threads.restype = None
+    lib.synth_set_threads(usable_cores())
     lib.synth_fill_bf16.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float]
     lib.synth_fill_bf16.restype = None
     lib.synth_fill_f16.argtypes = lib.synth_fill_bf16.argtypes

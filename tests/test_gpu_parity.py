@@ -3,6 +3,8 @@ same seeded inputs.  Tolerances are stated where used.
 
 Reference contract restated here: "An inference engine should work the same for any number of Shards"
 (/root/reference/xotorch/inference/test_inference_engine.py:11,43-44 -> np.array_equal(full, sharded))."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -374,3 +376,89 @@ def test_forward_device_equals_host_buffer_forward(shape_name):
   got2 = b2.forward_device(None, h1.data_ptr(), 1, 150, None)
   assert np.array_equal(got, want) and np.array_equal(got2, want2)
 
+
+
+def test_streaming_loader_chunks_equal_device_synth_at_real_dims(tmp_path):
+  """The streaming shard loader (mmap -> pinned double buffer -> DMA -> re-layout kernel, 64 MiB chunks) on tensors that need
+  several chunks: Llama-3-8B dimensions, 1 layer + embedding + head (2.5 GB: embed/head 1 GB = 16 plain / K-panel chunks,
+  gate/up 117 MB = 2 chunks into interleaved rows, q/k 32 MB with the head-wise _permute).  Bit-exact against the device
+  generator, and the load rate is reported next to the round-1 per-tensor path (XOTB200_LOAD_STREAM=0)."""
+  import dataclasses, json, os, time
+  from xotorch_b200.native import NativeShard
+  shape = dataclasses.replace(PRESETS["llama-3-8b"], n_layers=1, name="llama-3-8b-cut1")
+  d = write_hf_dir(tmp_path / "m", shape, 1234, n_files=2)
+  prompt = synth_prompt(shape.vocab, 9)
+  a = NativeShard(hf_config(shape), 0); a.set_shard(0, 0); a.init_synthetic(1234)
+  want = _api_generate([a], prompt, 3)
+  a.close()
+  rates = {}
+  for mode in ("1", "0"):
+    os.environ["XOTB200_LOAD_STREAM"] = mode
+    try:
+      b = NativeShard(hf_config(shape), 0)
+      t0 = time.time()
+      b.load_dir(d, 0, 0)
+      st = b.load_stats()
+      rates["streaming" if mode == "1" else "per-tensor (round 1)"] = {"GBps": round(st["GBps"], 2), "seconds": round(time.time() - t0, 2),
+                                                                          "bytes": st["bytes"], "memcpy_seconds": round(st["memcpy_seconds"], 2)}
+      got = _api_generate([b], prompt, 3)
+      b.close()
+    finally:
+      os.environ.pop("XOTB200_LOAD_STREAM", None)
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]), f"loader mode {mode}"
+  print(f"[loader] {json.dumps(rates)}")
+  out = Path(__file__).resolve().parent.parent / "gpurun_out"
+  if out.is_dir():
+    (out / "loader_rates.json").write_text(json.dumps(rates, indent=1))
+
+
+def _rewrite_safetensors(path, mutate):
+  """re-serialise one safetensors file after `mutate(header_dict, data_bytes) -> (header_dict, data_bytes)`"""
+  import json, struct
+  raw = Path(path).read_bytes()
+  hlen = struct.unpack("<Q", raw[:8])[0]
+  hdr, data = json.loads(raw[8:8 + hlen]), raw[8 + hlen:]
+  hdr, data = mutate(hdr, data)
+  hb = json.dumps(hdr, separators=(",", ":")).encode()
+  Path(path).write_bytes(struct.pack("<Q", len(hb)) + hb + data)
+
+
+def test_strict_loader_rejects_malformed_and_foreign_tensors(tmp_path):
+  """a biased-attention checkpoint (tensor of an owned layer the engine has no use for) and a file whose
+  data_offsets do not match the declared shape / the file size must be refused, not silently loaded."""
+  import shutil
+  from xotorch_b200.native import NativeShard
+  from xotorch_b200._lib import XotB200Error
+  shape = PRESETS["tiny-llama-hd64"]
+  good = write_hf_dir(tmp_path / "good", shape, 1234, n_files=1)
+  f = next(Path(good).glob("*.safetensors")).name
+
+  def variant(name, mutate):
+    d = tmp_path / name
+    shutil.copytree(good, d)
+    _rewrite_safetensors(d / f, mutate)
+    return d
+
+  def add_bias(h, data):
+    h["model.layers.1.self_attn.q_proj.bias"] = {"dtype": "BF16", "shape": [shape.n_heads * shape.head_dim], "data_offsets": [len(data), len(data) + 2 * shape.n_heads * shape.head_dim]}
+    return h, data + b"\0" * (2 * shape.n_heads * shape.head_dim)
+
+  def short_offsets(h, data):
+    e = h["model.layers.0.mlp.down_proj.weight"]
+    e["data_offsets"] = [e["data_offsets"][0], e["data_offsets"][1] - 64]
+    return h, data
+
+  def past_eof(h, data):
+    e = h["model.layers.0.mlp.down_proj.weight"]
+    n = e["data_offsets"][1] - e["data_offsets"][0]
+    e["data_offsets"] = [len(data) - 16, len(data) - 16 + n]
+    return h, data
+
+  e = NativeShard(hf_config(shape), 0)
+  e.load_dir(good, 0, shape.n_layers - 1)                     # the untouched directory loads
+  with pytest.raises(XotB200Error, match="no use for it"):
+    e.load_dir(variant("bias", add_bias), 0, shape.n_layers - 1)
+  e.load_dir(variant("bias_elsewhere", add_bias), 2, 3)       # ... but a shard that does not own layer 1 is not concerned
+  for name, mut in (("short", short_offsets), ("eof", past_eof)):
+    with pytest.raises(XotB200Error, match="data_offsets"):
+      e.load_dir(variant(name, mut), 0, shape.n_layers - 1)

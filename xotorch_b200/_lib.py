@@ -58,6 +58,10 @@ _SIGS = {
   "xotb200_link_next_local": (C.c_int, [C.c_void_p, C.c_void_p]),
   "xotb200_post_to_next": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_ring_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+  "xotb200_ring_launch_slots": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+  "xotb200_post_token": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int]),
+  "xotb200_ring_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+  "xotb200_clear_request": (C.c_int, [C.c_void_p, C.c_int]),
   "xotb200_ring_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
   "xotb200_ring_next_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
   "xotb200_ring_timestamps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -67,6 +71,7 @@ _SIGS = {
   "xotb200_debug_routing": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int]),
   "xotb200_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
   "xotb200_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+  "xotb200_load_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
   "xotb200_weight_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
   "xotb200_step_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
 }

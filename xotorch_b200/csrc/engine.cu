@@ -27,6 +27,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <map>
 #include <mutex>
 #include <string>
@@ -130,6 +133,7 @@ struct xotb200_engine {
   float* cta_best_val = nullptr;
   int* cta_best_idx = nullptr;
   int nsplit = 1, nsplit_min = 1;
+  int attn_l2_prefetch = 3;        // bit 0: K/V of the step's attention items, bit 1: the next RMSNorm scale vectors (XOTB200_ATTN_L2PF: A/B)
   int attn_direct_max = 1024;      // see AttnPlan in megakernel_impl.inc (XOTB200_ATTN_DIRECT_MAX: tuning hook, 0 = always split)
   StepCtl* ctl = nullptr;
   InboxHdr* inbox = nullptr;
@@ -142,6 +146,14 @@ struct xotb200_engine {
   bf16* hop_buf[API_SLOTS] = {};           // receiver side: [n_tokens, D] prompt hidden states pushed by the previous engine
   int hop_cap[API_SLOTS] = {};
   int hop_in = 0, hop_out = 0;             // per-launch arguments of the API hop (see MegaArgs)
+  // continuous batching: the active requests of the next ring launch (KV slot + position each); NULL/0 = all nreq from pos0
+  int *d_req_map = nullptr, *d_pos_tab = nullptr;
+  int n_active = 0;
+  // generated tokens streamed to the host while the persistent kernel runs (pinned, mapped)
+  int* tok_host = nullptr;
+  int* tok_host_dev = nullptr;
+  volatile unsigned int* tok_count_host = nullptr;
+  unsigned int* tok_count_dev = nullptr;
   unsigned int hop_seq_in = 0, hop_seq_out = 0;
   int* tokens_log = nullptr;
   int* route_log = nullptr;         // sparse MoE: experts chosen per (position, local layer) of request 0
@@ -175,6 +187,8 @@ struct xotb200_engine {
   int dbg_step = -1, dbg_cta = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
+  int64_t load_bytes = 0;          // xotb200_load_shard: bytes moved host -> HBM, wall seconds, seconds spent copying out of the mapping
+  double load_seconds = 0.0, load_memcpy_seconds = 0.0;
   int last_ring_steps = 0;
   int ring_next_step = 0;          // first ring step number no run on this engine has used (inbox flags are never reused)
 };
@@ -269,6 +283,7 @@ static int prepare_mega(xotb200_engine* e) {
   if (const char* v = getenv("XOTB200_NSPLIT_MIN")) e->nsplit_min = std::max(1, atoi(v));
   e->nsplit_min = std::min(e->nsplit_min, e->nsplit);
   if (const char* v = getenv("XOTB200_ATTN_DIRECT_MAX")) e->attn_direct_max = std::max(0, atoi(v));
+  if (const char* v = getenv("XOTB200_ATTN_L2PF")) e->attn_l2_prefetch = atoi(v);
   return 0;
 }
 
@@ -286,11 +301,16 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.x = e->x; a.q = e->q; a.attn_out = e->attn_out; a.act = e->act; a.logits = e->logits;
   a.part_ml = e->part_ml; a.part_acc = e->part_acc; a.tickets = e->tickets;
   a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit; a.nsplit_min = e->nsplit_min;
-  a.attn_direct_max = e->attn_direct_max;
+  a.attn_direct_max = e->attn_direct_max; a.attn_l2_prefetch = e->attn_l2_prefetch;
   a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
   a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
-  a.nreq = e->nreq; a.nslots = e->nreq + 1; a.req0 = e->cur_req; a.kv_req_stride = e->kv_req_stride;
+  const int nact = (mode == 0 && e->n_active > 0) ? e->n_active : e->nreq;
+  a.nreq = nact; a.nslots = nact + 1; a.req0 = e->cur_req; a.kv_req_stride = e->kv_req_stride;
+  a.req_map = (mode == 0 && e->n_active > 0) ? e->d_req_map : nullptr;
+  a.pos_tab = (mode == 0 && e->n_active > 0) ? e->d_pos_tab : nullptr;
+  a.tok_host = (mode == 0 && e->last) ? e->tok_host_dev : nullptr;
+  a.tok_count_host = e->tok_count_dev;
   a.src_tokens = e->stage_tokens; a.src_hidden = e->stage_in; a.out_hidden = e->stage_out;
   a.hop_in = mode == 1 ? e->hop_in : 0; a.hop_out = mode == 1 ? e->hop_out : 0;
   a.hop_seq_in = e->hop_seq_in; a.hop_seq_out = e->hop_seq_out;
@@ -418,8 +438,10 @@ static int launch_tc_gemm_persistent(xotb200_engine* e, const CUtensorMap& tmA, 
   return 0;
 }
 
-static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a, int epi, TcCfg c,
+static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a_in, int epi, TcCfg c,
                           cudaStream_t st) {
+  TcGemmArgs a = a_in;
+  a.err = &e->ctl->err;
   REQUIRE(a.N % c.nt == 0 && a.K % TC_BK == 0, "tensor-core GEMM needs N %% %d == 0 and K %% 64 == 0 (N=%d K=%d)", c.nt, a.N, a.K);
   {
     static const bool persist = !(getenv("XOTB200_TC_PERSIST") && atoi(getenv("XOTB200_TC_PERSIST")) == 0);
@@ -737,6 +759,89 @@ static int upload_slot(xotb200_engine* e, TensorSlot& s, const void* host) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// Streaming shard loader: safetensors file (mmap, page cache) -> pinned double buffer -> HBM.
+// The reference reads every *.safetensors of the directory fully into host tensors and copies module by module
+// (llm_utils.py:205-218,230-318).  Here a tensor is cut into chunks of whole rows (<= STAGE_BYTES); worker threads copy chunk
+// i+1 from the mapping into pinned buffer B while chunk i goes pinned buffer A -> device (DMA at PCIe rate, no pageable bounce
+// through the driver's staging buffer) -> row re-layout kernel -> its place in the weight blob.  No per-tensor cudaMalloc /
+// cudaFree / stream synchronise; one synchronise per file.
+// --------------------------------------------------------------------------------------------------------------
+struct StreamLoader {
+  static constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+  xotb200_engine* e = nullptr;
+  void* pinned[2] = {nullptr, nullptr};
+  bf16* dtemp[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};      // buffer i may be overwritten once done[i] has completed
+  int cur = 0, nthreads = 4;
+  double t_memcpy = 0.0;
+  int64_t bytes = 0;
+
+  int init(xotb200_engine* eng) {
+    e = eng;
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaHostAlloc(&pinned[i], STAGE_BYTES, cudaHostAllocDefault));
+      CK(cudaMalloc(&dtemp[i], STAGE_BYTES));
+      CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    nthreads = (int)std::max(1u, std::min(8u, hc ? hc / 2 : 4u));
+    if (const char* v = getenv("XOTB200_LOAD_THREADS")) nthreads = std::max(1, std::min(32, atoi(v)));
+    return 0;
+  }
+  ~StreamLoader() {
+    for (int i = 0; i < 2; ++i) {
+      if (done[i]) cudaEventDestroy(done[i]);
+      if (dtemp[i]) cudaFree(dtemp[i]);
+      if (pinned[i]) cudaFreeHost(pinned[i]);
+    }
+  }
+  // parallel copy out of the file mapping (page-cache reads scale with threads; one thread tops out at a few GB/s)
+  void copy_in(void* dst, const void* src, size_t n) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int T = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, n >> 20));
+    if (T <= 1) memcpy(dst, src, n);
+    else {
+      std::vector<std::thread> th;
+      const size_t per = (n / T + 4095) & ~(size_t)4095;
+      for (int t = 0; t < T; ++t) {
+        const size_t a = (size_t)t * per, b = std::min(n, a + per);
+        if (a < b) th.emplace_back([=] { memcpy((char*)dst + a, (const char*)src + a, b - a); });
+      }
+      for (auto& x : th) x.join();
+    }
+    t_memcpy += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  // one tensor of the file into one destination slot
+  int upload(TensorSlot& s, const char* host) {
+    const size_t row_bytes = (size_t)s.K * 2;
+    const bool plain = s.mode == 0 && s.stride == 1 && s.panel_tk == 0;
+    int unit = s.mode == 1 ? e->cfg.head_dim : 1;                                   // q/k interleave permutes rows inside a head
+    int rows_per = (int)std::max<size_t>(1, STAGE_BYTES / row_bytes) / unit * unit;
+    REQUIRE(rows_per >= unit, "a block of %d rows of %d columns does not fit the %zu-byte staging buffer", unit, s.K, STAGE_BYTES);
+    for (int r0 = 0; r0 < s.rows; r0 += rows_per) {
+      const int rows = std::min(rows_per, s.rows - r0);
+      const size_t n = (size_t)rows * row_bytes;
+      CK(cudaEventSynchronize(done[cur]));                                           // previous use of this buffer pair finished
+      copy_in(pinned[cur], host + (size_t)r0 * row_bytes, n);
+      if (plain) {
+        CK(cudaMemcpyAsync(s.dst + (size_t)(s.off + r0) * s.K, pinned[cur], n, cudaMemcpyHostToDevice, e->stream));
+      } else {
+        CK(cudaMemcpyAsync(dtemp[cur], pinned[cur], n, cudaMemcpyHostToDevice, e->stream));
+        relayout_rows_kernel<<<rows, 128, 0, e->stream>>>(dtemp[cur], s.dst, rows, s.K, s.mode, e->cfg.head_dim, s.stride,
+                                                          s.off + r0 * s.stride, s.n_total, s.panel_tk);
+        CK(cudaGetLastError());
+        e->launches++;
+      }
+      CK(cudaEventRecord(done[cur], e->stream));
+      cur ^= 1;
+      bytes += (int64_t)n;
+    }
+    s.loaded = true;
+    return 0;
+  }
+};
+
+// --------------------------------------------------------------------------------------------------------------
 // C ABI
 // --------------------------------------------------------------------------------------------------------------
 extern "C" {
@@ -790,6 +895,19 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   CK(cudaMalloc(&e->inbox, inbox_bytes));
   MEMSET_SYNC(e, e->inbox, 0, inbox_bytes);
   CK(cudaMalloc(&e->tokens_log, MAX_RING_STEPS * 4));
+  CK(cudaMalloc(&e->d_req_map, INBOX_SLOTS * 4));
+  CK(cudaMalloc(&e->d_pos_tab, INBOX_SLOTS * 4));
+  {
+    void* hp = nullptr;
+    CK(cudaHostAlloc(&hp, (MAX_RING_STEPS + 16) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(hp, 0, (MAX_RING_STEPS + 16) * 4);
+    e->tok_host = static_cast<int*>(hp) + 16;                       // [0]: counter (own cache line), [16..]: token ids
+    e->tok_count_host = static_cast<volatile unsigned int*>(hp);
+    void* dp = nullptr;
+    CK(cudaHostGetDevicePointer(&dp, hp, 0));
+    e->tok_count_dev = static_cast<unsigned int*>(dp);
+    e->tok_host_dev = static_cast<int*>(dp) + 16;
+  }
   CK(cudaMalloc(&e->t_in, MAX_RING_STEPS * 8));
   CK(cudaMalloc(&e->t_out, MAX_RING_STEPS * 8));
   MEMSET_SYNC(e, e->t_in, 0, MAX_RING_STEPS * 8);
@@ -810,7 +928,8 @@ int xotb200_destroy(xotb200_engine* e) {
     if (p) cudaFree(p);
   for (bf16* p : e->hop_buf)
     if (p) cudaFree(p);
-  void* ptrs[] = {e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
+  if (e->tok_count_host) cudaFreeHost(const_cast<unsigned int*>(e->tok_count_host));
+  void* ptrs[] = {e->d_req_map, e->d_pos_tab, e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
                   e->cta_best_idx, e->ctl, e->bar_counter, e->dbg, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
                   e->stage_f32, e->stage_in, e->stage_out};
   for (void* p : ptrs)
@@ -945,6 +1064,13 @@ int xotb200_load_shard(xotb200_engine* e, const char* dir, int start_layer, int 
   closedir(d);
   std::sort(files.begin(), files.end());
   if (files.empty()) { set_err("no *.safetensors in %s", dir); return XOTB200_EIO; }
+  CK(cudaSetDevice(e->device));
+  const bool streaming = !(getenv("XOTB200_LOAD_STREAM") && atoi(getenv("XOTB200_LOAD_STREAM")) == 0);   // 0: the round-1 per-tensor path (A/B)
+  StreamLoader ld;
+  if (streaming)
+    if (int rc = ld.init(e)) return rc;
+  const auto t_load0 = std::chrono::steady_clock::now();
+  e->load_bytes = 0;
   for (auto& f : files) {
     int fd = open(f.c_str(), O_RDONLY);
     if (fd < 0) { set_err("cannot open %s", f.c_str()); return XOTB200_EIO; }
@@ -953,6 +1079,7 @@ int xotb200_load_shard(xotb200_engine* e, const char* dir, int start_layer, int 
     void* m = mmap(nullptr, sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (m == MAP_FAILED) { set_err("mmap failed for %s", f.c_str()); return XOTB200_EIO; }
+    posix_madvise(m, sb.st_size, POSIX_MADV_SEQUENTIAL);
     const char* base = static_cast<const char*>(m);
     uint64_t hlen = 0;
     memcpy(&hlen, base, 8);
@@ -988,12 +1115,32 @@ int xotb200_load_shard(xotb200_engine* e, const char* dir, int start_layer, int 
         rc = XOTB200_EIO;
         break;
       }
-      rc = xotb200_load_tensor(e, it->first.c_str(), base + 8 + hlen + en.begin, en.shape.data(), (int)en.shape.size());
-      if (rc == 1) rc = 0;
+      const char* data = base + 8 + hlen + en.begin;
+      if (!streaming) {
+        rc = xotb200_load_tensor(e, it->first.c_str(), data, en.shape.data(), (int)en.shape.size());
+        if (rc == 1) rc = 0;
+        e->load_bytes += en.end - en.begin;
+        continue;
+      }
+      const int64_t rows = en.shape.size() == 2 ? en.shape[0] : 1, K = en.shape.size() == 2 ? en.shape[1] : en.shape[0];
+      auto range = e->slots.equal_range(it->first);
+      for (auto sl2 = range.first; rc == 0 && sl2 != range.second; ++sl2) {       // a tied embedding feeds two destinations
+        TensorSlot& ts = sl2->second;
+        if (rows != ts.rows || K != ts.K) {
+          set_err("tensor %s: shape mismatch (got %lld x %lld, want %d x %d)", it->first.c_str(), (long long)rows, (long long)K, ts.rows, ts.K);
+          rc = XOTB200_EINVAL;
+          break;
+        }
+        rc = ld.upload(ts, data);
+      }
     }
-    munmap(m, sb.st_size);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess && rc == 0) { set_err("stream error while loading %s", f.c_str()); rc = XOTB200_ECUDA; }
+    munmap(m, sb.st_size);                        // only after every copy out of the mapping has completed
     if (rc) return rc;
   }
+  if (streaming) e->load_bytes = ld.bytes;
+  e->load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load0).count();
+  e->load_memcpy_seconds = ld.t_memcpy;
   return xotb200_check_loaded(e);
 }
 
@@ -1096,6 +1243,19 @@ int xotb200_select_request(xotb200_engine* e, int request) {
   return 0;
 }
 
+// sticky device-side error word -> status code (3: a bounded wait inside the persistent tensor-core GEMM expired)
+static int check_device_error(xotb200_engine* e) {
+  StepCtl h;
+  CK(cudaMemcpyAsync(&h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (h.err) {
+    MEMSET_SYNC(e, &e->ctl->err, 0, 4);
+    set_err(h.err == 3 ? "tensor-core GEMM: a pipeline wait expired (device error %d)" : "device-side wait timed out (device error %d)", h.err);
+    return XOTB200_ETIMEOUT;
+  }
+  return 0;
+}
+
 static int ensure_staging(xotb200_engine* e, int n) {
   if (n <= e->stage_cap) return 0;
   const size_t D = e->cfg.dim;
@@ -1151,6 +1311,8 @@ int xotb200_forward(xotb200_engine* e, const int32_t* tokens, const float* hidde
     CK(cudaMemcpyAsync(out_f32, e->stage_f32, (size_t)n_tokens * D * 4, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  if (use_tc)
+    if (int rc = check_device_error(e)) return rc;
   e->have_result = true;
   return 0;
 }
@@ -1358,11 +1520,76 @@ int xotb200_ring_launch(xotb200_engine* e, int n_steps, int step0, int pos0) {
   if (int rc = xotb200_check_loaded(e)) return rc;
   CK(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
+  CK(cudaStreamSynchronize(st));                 // the previous run's kernel must not still be writing the host token log
+  *e->tok_count_host = 0;
   CK(cudaEventRecord(e->ev0, st));
   if (int rc = launch_mega(e, 0, n_steps, step0, pos0, st)) return rc;
   CK(cudaEventRecord(e->ev1, st));
   e->last_ring_steps = n_steps;
   e->ring_next_step = std::max(e->ring_next_step, step0 + n_steps);
+  return 0;
+}
+
+// Continuous batching: a ring launch over an explicit set of ACTIVE requests, each with its own KV slot and its
+// own position — requests join (after a prefill into a free slot) and leave between launches, the others keep their caches.
+int xotb200_ring_launch_slots(xotb200_engine* e, int n_steps, int step0, const int32_t* kv_slots, const int32_t* positions, int n_active) {
+  REQUIRE(e && kv_slots && positions, "null argument");
+  REQUIRE(n_active >= 1 && n_active <= e->nreq, "n_active %d out of range (batch of %d KV caches)", n_active, e ? e->nreq : 0);
+  REQUIRE(n_steps >= 1 && n_steps % n_active == 0, "n_steps %d must be a positive multiple of the %d active requests", n_steps, n_active);
+  for (int i = 0; i < n_active; ++i) {
+    REQUIRE(kv_slots[i] >= 0 && kv_slots[i] < e->nreq, "kv slot %d out of range", kv_slots[i]);
+    REQUIRE(positions[i] >= 0 && positions[i] + n_steps / n_active <= e->L, "request in slot %d: position %d + %d tokens exceeds the KV capacity %d",
+            kv_slots[i], positions[i], n_steps / n_active, e->L);
+    for (int j = 0; j < i; ++j) REQUIRE(kv_slots[j] != kv_slots[i], "kv slot %d named twice", kv_slots[i]);
+  }
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(e->d_req_map, kv_slots, (size_t)n_active * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_pos_tab, positions, (size_t)n_active * 4, cudaMemcpyHostToDevice, e->stream));
+  e->n_active = n_active;
+  const int saved_nreq = e->nreq;
+  e->nreq = n_active;                       // the divisibility / capacity checks of xotb200_ring_launch apply to the active set
+  const int rc = xotb200_ring_launch(e, n_steps, step0, 0);
+  e->nreq = saved_nreq;
+  e->n_active = 0;
+  return rc;
+}
+
+// Tokens the last shard has produced so far in the CURRENT ring launch, readable while the persistent kernel is still running
+// (the kernel writes them to pinned, mapped host memory): what a Node.on_token bridge streams from (node.py:119-147).
+int xotb200_ring_poll(xotb200_engine* e, int32_t* tokens_out, int from, int max_n, int* n_done) {
+  REQUIRE(e && n_done && from >= 0 && max_n >= 0, "bad argument");
+  REQUIRE(e->last, "tokens are produced on the last shard");
+  const unsigned int done = *e->tok_count_host;
+  std::atomic_thread_fence(std::memory_order_acquire);
+  const int avail = std::max(0, std::min((int)done - from, max_n));
+  if (tokens_out)
+    for (int i = 0; i < avail; ++i) tokens_out[i] = e->tok_host[from + i];
+  *n_done = (int)done;
+  return 0;
+}
+
+// Seed ring step `step` of the FIRST shard with an explicit token id (this engine is the last shard; `n_active` requests will be
+// in flight in the run that consumes it).  Used when the set of active requests changes between launches.
+int xotb200_post_token(xotb200_engine* e, int step, int32_t token, int n_active) {
+  REQUIRE(e && e->next_inbox, "next inbox not linked");
+  REQUIRE(e->last, "tokens are posted by the last shard");
+  REQUIRE(step >= 0 && n_active >= 1 && n_active <= INBOX_SLOTS - 1 && token >= 0 && token < e->cfg.vocab, "bad argument");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(e->d_pos_tab + INBOX_SLOTS - 1, &token, 4, cudaMemcpyHostToDevice, e->stream));   // scratch word
+  post_kernel<<<1, 32, 0, e->stream>>>(e->next_inbox, nullptr, e->cfg.dim, e->d_pos_tab + INBOX_SLOTS - 1, step, n_active + 1);
+  CK(cudaGetLastError());
+  e->launches++;
+  e->ring_next_step = std::max(e->ring_next_step, step + 1);
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// Zero the KV cache of one request slot (what reset_caches does for the reference's single request, llm_utils.py:409-414).
+int xotb200_clear_request(xotb200_engine* e, int request) {
+  REQUIRE(e && e->kv && request >= 0 && request < e->nreq, "request index out of range");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(e->kv + (size_t)request * e->kv_req_stride, 0, e->kv_req_stride * 2, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
 
@@ -1478,6 +1705,12 @@ int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, 
 int xotb200_kernel_launches(xotb200_engine* e, int64_t* count) {
   REQUIRE(e && count, "null argument");
   *count = e->launches;
+  return 0;
+}
+
+int xotb200_load_stats(xotb200_engine* e, int64_t* bytes, double* seconds, double* memcpy_seconds) {
+  REQUIRE(e && bytes && seconds && memcpy_seconds, "null argument");
+  *bytes = e->load_bytes; *seconds = e->load_seconds; *memcpy_seconds = e->load_memcpy_seconds;
   return 0;
 }
 

@@ -67,6 +67,7 @@ struct MegaArgs {
   float* cta_best_val;
   int* cta_best_idx;
   int nsplit, nsplit_min;   // context splits per kv head: upper bound (CTAs / kv heads) and the count used for short contexts
+  int attn_l2_prefetch;     // bit 0: K/V of the step's attention items, bit 1: the next RMSNorm scales -> L2 at the start of the QKV op
   int attn_direct_max;      // contexts up to this length: one CTA per QUERY head does the whole attention (no split partials / ticket)
   StepCtl* ctl;
   InboxHdr *inbox, *next_inbox;
@@ -82,6 +83,10 @@ struct MegaArgs {
   int nreq;                  // requests in flight (ring mode): ring step s serves request s % nreq at position pos0 + s / nreq
   int nslots;                // inbox slots in use = nreq + 1 (a shard is never more than nreq-1 steps ahead of the next one)
   int req0;                  // direct mode: the request whose KV cache this call works on
+  const int* req_map;        // ring mode, optional [nreq]: KV cache of the i-th active request (NULL: i)
+  const int* pos_tab;        // ring mode, optional [nreq]: position of the i-th active request's first step of this launch (NULL: pos0)
+  int* tok_host;             // last shard, optional: host-mapped token log [MAX_RING_STEPS] + counter, readable while the kernel runs
+  unsigned int* tok_count_host;
   size_t kv_req_stride;      // elements between the KV caches of consecutive requests
   const int* src_tokens;     // direct, first shard: [n_steps]
   const bf16* src_hidden;    // direct, other shards: [n_steps, D]

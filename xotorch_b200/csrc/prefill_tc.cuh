@@ -37,6 +37,7 @@ struct TcGemmArgs {
   int mt0;          // first token tile of this launch (0, or the last tile for HEAD_LAST)
   const int* tile_info;   // sparse MoE (NULL otherwise): {first row of this expert's block, its 128-row tiles}; CTAs beyond exit
   int grid_m;             // sparse MoE: token tiles to launch (the most one expert can get); 0 = ceil(S / 128) - mt0
+  int* err;               // sticky device error word (StepCtl::err): 3 = a bounded wait of the persistent GEMM expired
 };
 
 __host__ __device__ constexpr int tc_stage_bytes(int nt) { return TC_M * TC_BK * 2 + nt * TC_BK * 2; }

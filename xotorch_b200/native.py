@@ -210,6 +210,26 @@ class NativeShard:
       check(self.lib.xotb200_ring_wait(self.h, None, 0, C.byref(ms)))
     return toks, float(ms.value)
 
+  def ring_launch_slots(self, n_steps: int, step0: int, kv_slots, positions):
+    """ring launch over an explicit set of active requests: request i lives in KV cache kv_slots[i] at position positions[i]"""
+    sl = np.ascontiguousarray(kv_slots, dtype=np.int32); ps = np.ascontiguousarray(positions, dtype=np.int32)
+    assert sl.shape == ps.shape and sl.ndim == 1
+    check(self.lib.xotb200_ring_launch_slots(self.h, int(n_steps), int(step0), sl.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p), int(sl.size)))
+
+  def post_token(self, step: int, token: int, n_active: int):
+    check(self.lib.xotb200_post_token(self.h, int(step), int(token), int(n_active)))
+
+  def ring_poll(self, start: int = 0, max_n: int = 4096) -> Tuple[np.ndarray, int]:
+    """(token ids [start : done) produced so far by the running ring launch, done) — does not wait, safe while the kernel runs"""
+    buf = np.empty(max(max_n, 1), dtype=np.int32)
+    done = C.c_int()
+    check(self.lib.xotb200_ring_poll(self.h, buf.ctypes.data_as(C.c_void_p), int(start), int(max_n), C.byref(done)))
+    n = max(0, min(int(done.value) - start, max_n))
+    return buf[:n].copy(), int(done.value)
+
+  def clear_request(self, request: int):
+    check(self.lib.xotb200_clear_request(self.h, int(request)))
+
   def ring_next_step(self) -> int:
     """first ring step number not yet used on this engine (inbox flags are monotonic and never cleared)"""
     v = C.c_int()
@@ -260,6 +280,13 @@ class NativeShard:
     v = C.c_int64()
     check(self.lib.xotb200_kernel_launches(self.h, C.byref(v)))
     return int(v.value)
+
+  def load_stats(self) -> dict:
+    """the most recent load_dir: bytes into HBM, wall seconds, GB/s, and the seconds spent copying out of the file mapping"""
+    b, t, tm = C.c_int64(), C.c_double(), C.c_double()
+    check(self.lib.xotb200_load_stats(self.h, C.byref(b), C.byref(t), C.byref(tm)))
+    return {"bytes": int(b.value), "seconds": float(t.value), "GBps": (b.value / t.value / 1e9) if t.value > 0 else 0.0,
+            "memcpy_seconds": float(tm.value)}
 
   def weight_bytes(self) -> int:
     v = C.c_int64()

@@ -67,6 +67,66 @@ class HBMWeightedRingPartitioningStrategy(RingMemoryWeightedPartitioningStrategy
     return out
 
 
+def model_stream_bytes(hf_config: dict) -> Tuple[int, int]:
+  """(bytes one decoder layer streams per decoded token, bytes the last shard streams on top: final norm + lm_head), 16-bit
+  weights, from an HF config.json dict — SURVEY.md §8d's per-token byte formula (sparse MoE: the active experts only)."""
+  D, F = hf_config["hidden_size"], hf_config["intermediate_size"]
+  Hq, Hkv = hf_config["num_attention_heads"], hf_config["num_key_value_heads"]
+  hd = hf_config.get("head_dim") or D // Hq
+  E, k = int(hf_config.get("num_local_experts") or 0), int(hf_config.get("num_experts_per_tok") or 0)
+  mlp = (E * D + k * 3 * D * F) if E else 3 * D * F
+  layer = 2 * (D * Hq * hd + 2 * D * Hkv * hd + Hq * hd * D + mlp + 2 * D)
+  head = 2 * (hf_config["vocab_size"] * D + D)
+  return layer, head
+
+
+class ByteBalancedRingPartitioningStrategy(RingMemoryWeightedPartitioningStrategy):
+  """Ring partition that balances the BYTES A SHARD STREAMS PER TOKEN (= its decode time on an HBM-bound engine) instead of
+  the layer count: the last shard also streams final norm + lm_head (1.05 GB for Llama-3-8B = 2.4 decoder layers), so under
+  the reference rule it sets the period of a ring with several requests in flight (8B on 8 GPUs: 2.79 GB vs
+  1.74 GB elsewhere).  Same node order as the reference ((memory, id) descending) and the same `Partition` fractions ->
+  `map_partitions_to_shards` pipeline, so every node still derives the same ranges; node i's share of the bytes is its share
+  of the memory.  Boundaries are whole layers: cumulative byte target T_i -> the layer count nearest to it (each node keeps
+  at least one layer); the fraction handed to map_partitions_to_shards is (layers + 0.5) / n so its floor is exact.
+  8B / 8 equal GPUs: 4,5,4,4,5,4,4,2 layers (max 2.18 GB vs 2.79 GB); 8B / 2: 17 + 15; with head_bytes = 0 and a model whose
+  layers divide evenly it reproduces the reference's ranges."""
+
+  def __init__(self, n_layers: int, layer_bytes: int, head_bytes: int):
+    self.n_layers, self.layer_bytes, self.head_bytes = int(n_layers), int(layer_bytes), int(head_bytes)
+
+  @classmethod
+  def for_model(cls, hf_config: dict) -> "ByteBalancedRingPartitioningStrategy":
+    layer, head = model_stream_bytes(hf_config)
+    return cls(hf_config["num_hidden_layers"], layer, head)
+
+  def layer_counts(self, weights: List[float]) -> List[int]:
+    n, N = self.n_layers, len(weights)
+    if N > n:
+      raise ValueError(f"{N} nodes but only {n} layers")
+    total = n * self.layer_bytes + self.head_bytes
+    wsum = float(sum(weights))
+    bounds, cum, prev = [], 0.0, 0
+    for i in range(N - 1):
+      cum += weights[i] / wsum
+      k = int(round(cum * total / self.layer_bytes))          # cumulative layers whose bytes are nearest to the target
+      k = max(prev + 1, min(k, n - (N - 1 - i)))              # every node keeps at least one layer
+      bounds.append(k)
+      prev = k
+    bounds.append(n)
+    return [b - a for a, b in zip([0] + bounds[:-1], bounds)]
+
+  def partition(self, topology) -> List[Partition]:
+    nodes = sorted(_nodes(topology), key=lambda kv: (kv[1], kv[0]), reverse=True)
+    counts = self.layer_counts([m for _, m in nodes])
+    out, start, cum = [], 0, 0
+    for i, ((nid, _), k) in enumerate(zip(nodes, counts)):
+      cum += k
+      end = 1.0 if i == len(nodes) - 1 else round((cum + 0.5) / self.n_layers, 5)
+      out.append(Partition(nid, start, end))
+      start = end
+    return out
+
+
 def map_partitions_to_shards(partitions: List[Partition], num_layers: int, model_id: str) -> List[Shard]:
   shards: List[Shard] = []
   last = len(partitions) - 1
