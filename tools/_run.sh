@@ -1,10 +1,8 @@
 set -x
-qb() { timeout 300 python tools/quick_bench.py llama-3-8b 128 512 0 > gpurun_out/qb_$1.log 2>&1; echo "=== $1"; grep -E '"iter": 2|^qkv  |^gu  |attention chain|step total|Error|error' gpurun_out/qb_$1.log | cut -c1-330; }
-XOTB200_ATTN_L2PF=3 XOTB200_ATTN_DIRECT_MAX=1024 qb pf3_direct
-XOTB200_ATTN_L2PF=7 XOTB200_ATTN_DIRECT_MAX=1024 qb pf7_direct
-XOTB200_ATTN_L2PF=11 XOTB200_ATTN_DIRECT_MAX=1024 qb pf11_direct
-XOTB200_ATTN_L2PF=8 XOTB200_ATTN_DIRECT_MAX=1024 qb pf8_direct
-XOTB200_ATTN_L2PF=0 XOTB200_ATTN_DIRECT_MAX=1024 qb pf0_direct
-XOTB200_ATTN_L2PF=11 XOTB200_ATTN_DIRECT_MAX=0 qb pf11_split
-XOTB200_ATTN_L2PF=0 XOTB200_ATTN_DIRECT_MAX=0 qb pf0_split
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scheduler.py tests/test_gpu_node_ring.py -x -q 2>&1 | tail -3
+qb() { timeout 300 python tools/quick_bench.py llama-3-8b 128 512 0 > gpurun_out/qb_$1.log 2>&1; echo "=== $1"; grep -E '"iter": 2|^qkv  |attention chain|step total|Error|error' gpurun_out/qb_$1.log | cut -c1-330; }
+qb merge8
+XOTB200_NSPLIT_MIN=8 qb merge8_ns8
+XOTB200_NSPLIT_MIN=6 qb merge8_ns6
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_depth.py -x -q 2>&1 | tail -3

@@ -48,5 +48,28 @@ def full(path):
         print(f"    {k:95s} {row[h.index(k)]} {units[h.index(k)]}")
 
 
+def traffic(path, tokens, command):
+  """profiles/r2_decode_ncu_traffic.json (what bench.py reports as roofline.traffic): DRAM bytes per decoded token of the
+  persistent decode kernel = (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch / the tokens that launch decoded."""
+  import json
+  r = list(csv.reader(open(path)))
+  h, units = r[0], r[1]
+  row = [x for x in r[2:] if "shard_step_kernel" in x[h.index("Kernel Name")]][0]
+
+  def val(k):
+    v, u = float(row[h.index(k)].replace(",", "")), units[h.index(k)]
+    return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1.0)
+  rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+  dur = float(row[h.index("gpu__time_duration.sum")].replace(",", "")) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}[units[h.index("gpu__time_duration.sum")]]
+  out = {"bytes_per_token": int((rd + wr) / tokens), "dram_read_bytes": int(rd), "dram_write_bytes": int(wr), "tokens_in_launch": tokens,
+         "kernel": row[h.index("Kernel Name")].split("(")[0], "duration_ms_under_ncu": round(dur * 1e3, 3), "command": command,
+         "note": f"bytes per token = (dram__bytes_read.sum + dram__bytes_write.sum) / {tokens} tokens of one persistent-kernel launch, ncu --set full "
+                 f"--clock-control none of the committed build (profiles/r2_decode_ncu_full_metrics.txt)"}
+  print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-  {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+  if sys.argv[1] == "traffic":
+    traffic(sys.argv[2], int(sys.argv[3]), sys.argv[4] if len(sys.argv) > 4 else "")
+  else:
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

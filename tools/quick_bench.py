@@ -58,4 +58,7 @@ if len(sys.argv) > 4:   # timeline of one ring step
     print(names[k], "stage arrival (us after consume start):", [round((v - t0) / 1e3, 2) for v in row[:16]])
   st = stg[0][48:54]; t2 = tl[20, 2]
   print("attention chain (layer 5, CTA %s): tiles done -> B1 exit %.2f | K/V+softmax loop %.2f | warp+smem merge, partial store %.2f | ticket %.2f | (last CTA) split merge %.2f | B2 %.2f us" % ((sys.argv[4],) + tuple(round(x / 1e3, 2) for x in [st[0] - t2, st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4]])))
+  rr = stg[0][54:64]; rr = rr[rr > 0]
+  if len(rr):
+    print("direct attention rounds (us after B1 exit):", [round((v - st[0]) / 1e3, 2) for v in rr], " loop end:", round((st[1] - st[0]) / 1e3, 2))
   print("step total us", (tl[-1, 3] - tl[0, 0]) / 1e3, " sum prologue", pro.sum() / 1e3, " tiles", tiles.sum() / 1e3, " barrier", bar.sum() / 1e3)

@@ -133,8 +133,6 @@ struct xotb200_engine {
   float* cta_best_val = nullptr;
   int* cta_best_idx = nullptr;
   int nsplit = 1, nsplit_min = 1;
-  int attn_l2_prefetch = 3;        // bit 0: K/V of the step's attention items, bit 1: the next RMSNorm scale vectors (XOTB200_ATTN_L2PF: A/B)
-  int attn_direct_max = 1024;      // see AttnPlan in megakernel_impl.inc (XOTB200_ATTN_DIRECT_MAX: tuning hook, 0 = always split)
   StepCtl* ctl = nullptr;
   InboxHdr* inbox = nullptr;
   InboxHdr* next_inbox = nullptr;
@@ -172,6 +170,7 @@ struct xotb200_engine {
   int mega_xbuf = 0, mega_grid = 0, mega_nstage = 0;
   int cta_limit = 0;
   // tensor-core prefill (prefill_tc.cuh)
+  bool tc_fuse = true;             // RoPE/KV-append and SwiGLU fused into GEMM epilogues (XOTB200_TC_FUSE=0: separate kernels, A/B)
   int prefill_mode = 0;            // 0 auto (TC when n_tokens >= 8), 1 always the decode kernel, 2 always TC
   bf16 *tc_x = nullptr, *tc_xn = nullptr, *tc_qkv = nullptr, *tc_q = nullptr, *tc_ao = nullptr, *tc_gu = nullptr, *tc_act = nullptr;
   CUtensorMap tm_xn, tm_ao, tm_act;
@@ -282,8 +281,6 @@ static int prepare_mega(xotb200_engine* e) {
   if (const char* v = getenv("XOTB200_NSPLIT")) e->nsplit = std::max(1, std::min(e->nsplit, atoi(v)));   // tuning hooks
   if (const char* v = getenv("XOTB200_NSPLIT_MIN")) e->nsplit_min = std::max(1, atoi(v));
   e->nsplit_min = std::min(e->nsplit_min, e->nsplit);
-  if (const char* v = getenv("XOTB200_ATTN_DIRECT_MAX")) e->attn_direct_max = std::max(0, atoi(v));
-  if (const char* v = getenv("XOTB200_ATTN_L2PF")) e->attn_l2_prefetch = atoi(v);
   return 0;
 }
 
@@ -301,7 +298,6 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.x = e->x; a.q = e->q; a.attn_out = e->attn_out; a.act = e->act; a.logits = e->logits;
   a.part_ml = e->part_ml; a.part_acc = e->part_acc; a.tickets = e->tickets;
   a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit; a.nsplit_min = e->nsplit_min;
-  a.attn_direct_max = e->attn_direct_max; a.attn_l2_prefetch = e->attn_l2_prefetch;
   a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
   a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
@@ -411,6 +407,8 @@ static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CU
   switch (epi) {
     case TCE_STORE: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_STORE, NS> : xb::bf::tc_gemm_kernel<NT, TCE_STORE, NS>; break;
     case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_RESID, NS> : xb::bf::tc_gemm_kernel<NT, TCE_RESID, NS>; break;
+    case TCE_QKV: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_QKV, NS> : xb::bf::tc_gemm_kernel<NT, TCE_QKV, NS>; break;
+    case TCE_SWIGLU: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_SWIGLU, NS> : xb::bf::tc_gemm_kernel<NT, TCE_SWIGLU, NS>; break;
     default: fn = f16 ? xb::fp::tc_gemm_kernel<NT, TCE_HEAD_LAST, NS> : xb::bf::tc_gemm_kernel<NT, TCE_HEAD_LAST, NS>; break;
   }
   if (int rc = ensure_smem_attr(e->device, (const void*)fn, tc_smem_bytes(NT, NS))) return rc;
@@ -429,6 +427,8 @@ static int launch_tc_gemm_persistent(xotb200_engine* e, const CUtensorMap& tmA, 
   switch (epi) {
     case TCE_STORE: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_STORE, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_STORE, NS>; break;
     case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_RESID, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_RESID, NS>; break;
+    case TCE_QKV: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_QKV, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_QKV, NS>; break;
+    case TCE_SWIGLU: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_SWIGLU, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_SWIGLU, NS>; break;
     default: fn = f16 ? xb::fp::tc_gemm_persistent_kernel<NT, TCE_HEAD_LAST, NS> : xb::bf::tc_gemm_persistent_kernel<NT, TCE_HEAD_LAST, NS>; break;
   }
   if (int rc = ensure_smem_attr(e->device, (const void*)fn, tc_smem_bytes(NT, NS))) return rc;
@@ -582,10 +582,17 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
       bf16* vc = e->kv + (size_t)e->cur_req * e->kv_req_stride + ((size_t)li * 2 + 1) * Hkv * e->L * hd;
       DT_LAUNCH(e, (tc_rmsnorm_kernel<<<S, 256, 0, st>>>(e->tc_x, w.attn_norm, e->tc_xn, D, c.norm_eps)));
       CK(cudaGetLastError());
-      TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv, 0};
-      if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 0, g, TCE_STORE, st)) return rc;
-      DT_LAUNCH(e, (tc_rope_kv_kernel<<<S, 256, 0, st>>>(e->tc_qkv, e->tc_q, kc, vc, e->rope, Hq, Hkv, hd, e->L, pos0 + m0)));
-      CK(cudaGetLastError());
+      if (e->tc_fuse) {     // RoPE + KV append in the QKV GEMM's epilogue: rotated q -> tc_q, k / v -> the cache rows of this chunk
+        TcGemmArgs g{S, nqkv, D, e->tk, e->tc_q, nullptr, qd, 0};
+        g.kc = kc; g.vc = vc; g.rope = e->rope; g.q_rows = qd; g.kv_rows = Hkv * hd; g.hd = hd; g.L = e->L; g.pos0 = pos0 + m0;
+        if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 0, g, TCE_QKV, st)) return rc;
+      } else {
+        TcGemmArgs g{S, nqkv, D, e->tk, e->tc_qkv, nullptr, nqkv, 0};
+        if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 0, g, TCE_STORE, st)) return rc;
+        DT_LAUNCH(e, (tc_rope_kv_kernel<<<S, 256, 0, st>>>(e->tc_qkv, e->tc_q, kc, vc, e->rope, Hq, Hkv, hd, e->L, pos0 + m0)));
+        CK(cudaGetLastError());
+        e->launches++;
+      }
       if (int rc = (hd == 128 ? launch_tc_attn<128>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)
                               : launch_tc_attn<64>(e, S, Hq / Hkv, kc, vc, pos0 + m0, st)))
         return rc;
@@ -615,16 +622,22 @@ static int prefill_tc(xotb200_engine* e, int n_tokens, int pos0, cudaStream_t st
         }
         DT_LAUNCH(e, (moe_combine_kernel<<<S, 256, 0, st>>>(e->tc_x, e->moe_y, e->moe_row_of, e->moe_route_w, D)));
         CK(cudaGetLastError());
-        e->launches += 8;
+        e->launches += 7;   // 2 RMSNorm + router, plan, gather, SwiGLU, combine (RoPE/KV counted above when it is a kernel)
         continue;
       }
-      TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F, 0};
-      if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 2, u, TCE_STORE, st)) return rc;
-      DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F, nullptr)));
-      CK(cudaGetLastError());
+      if (e->tc_fuse) {     // SwiGLU in the gate/up GEMM's epilogue: [S, F] written instead of [S, 2F] + a kernel
+        TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_act, nullptr, F, 0};
+        if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 2, u, TCE_SWIGLU, st)) return rc;
+      } else {
+        TcGemmArgs u{S, 2 * F, D, e->tk, e->tc_gu, nullptr, 2 * F, 0};
+        if (int rc = tc_gemm(e, e->tm_xn, 4 * li + 2, u, TCE_STORE, st)) return rc;
+        DT_LAUNCH(e, (tc_swiglu_kernel<<<dim3(S, (F + 2047) / 2048), 256, 0, st>>>(e->tc_gu, e->tc_act, F, nullptr)));
+        CK(cudaGetLastError());
+        e->launches++;
+      }
       TcGemmArgs d{S, D, F, e->tk, e->tc_x, nullptr, D, 0};
       if (int rc = tc_gemm(e, e->tm_act, 4 * li + 3, d, TCE_RESID, st)) return rc;
-      e->launches += 4;
+      e->launches += 2;   // the two RMSNorm kernels (the GEMM / attention launchers count themselves)
     }
     if (e->last) {
       if (m0 + S == n_tokens) {   // logits of the last position only (sharded_inference_engine.py:365-368)
@@ -874,6 +887,7 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   e->sm_count = prop.multiProcessorCount;
   const int D = cfg->dim, Hq = cfg->n_heads, Hkv = cfg->n_kv_heads, hd = cfg->head_dim;
   e->nsplit = std::max(1, std::min(32, e->sm_count / Hkv));
+  if (const char* v = getenv("XOTB200_TC_FUSE")) e->tc_fuse = atoi(v) != 0;
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&e->ev0));
   CK(cudaEventCreate(&e->ev1));

@@ -67,8 +67,6 @@ struct MegaArgs {
   float* cta_best_val;
   int* cta_best_idx;
   int nsplit, nsplit_min;   // context splits per kv head: upper bound (CTAs / kv heads) and the count used for short contexts
-  int attn_l2_prefetch;     // bit 0: K/V of the step's attention items, bit 1: the next RMSNorm scales -> L2 at the start of the QKV op
-  int attn_direct_max;      // contexts up to this length: one CTA per QUERY head does the whole attention (no split partials / ticket)
   StepCtl* ctl;
   InboxHdr *inbox, *next_inbox;
   int* tokens_log;

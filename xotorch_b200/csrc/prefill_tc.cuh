@@ -23,7 +23,7 @@ constexpr int TC_M = 128;        // tokens per GEMM tile = UMMA M
 constexpr int TC_BK = 64;        // K elements per ring stage = one 128-byte swizzle row
 constexpr int TC_THREADS = 256;  // warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue
 
-enum { TCE_STORE = 0, TCE_RESID = 1, TCE_HEAD_LAST = 2 };
+enum { TCE_STORE = 0, TCE_RESID = 1, TCE_HEAD_LAST = 2, TCE_QKV = 3, TCE_SWIGLU = 4 };
 
 constexpr int TC_CHUNK = 1024;   // tokens per prefill pass: every weight tile is fetched from HBM once per chunk and reused
                                  // by the chunk's 128-token tiles out of L2 (grid x = token tile, so they run together)
@@ -37,6 +37,10 @@ struct TcGemmArgs {
   int mt0;          // first token tile of this launch (0, or the last tile for HEAD_LAST)
   const int* tile_info;   // sparse MoE (NULL otherwise): {first row of this expert's block, its 128-row tiles}; CTAs beyond exit
   int grid_m;             // sparse MoE: token tiles to launch (the most one expert can get); 0 = ceil(S / 128) - mt0
+  // TCE_QKV: RoPE + KV append fused into the QKV GEMM (out = rotated q [S, q_rows]); TCE_SWIGLU: out = act [S, N/2]
+  bf16 *kc, *vc;          // K / V cache of (request, layer): [Hkv][L][hd]
+  const float2* rope;     // [L][hd/2] (cos, sin)
+  int q_rows, kv_rows, hd, L, pos0;
   int* err;               // sticky device error word (StepCtl::err): 3 = a bounded wait of the persistent GEMM expired
 };
 
