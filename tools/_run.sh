@@ -1,8 +1,4 @@
 set -x
-qb() { timeout 300 python tools/quick_bench.py llama-3-8b 128 512 0 > gpurun_out/qb_$1.log 2>&1; echo "=== $1"; grep -E '"iter": 2|^qkv  |attention chain|step total|Error|error' gpurun_out/qb_$1.log | cut -c1-330; }
-qb merge8
-XOTB200_NSPLIT_MIN=8 qb merge8_ns8
-XOTB200_NSPLIT_MIN=6 qb merge8_ns6
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
-timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_depth.py -x -q 2>&1 | tail -3
+bash tools/_run_multi.sh 2
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --impl reference --gpus 2 --steps 4 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err; tail -c 2500 gpurun_out/bench_ref_n2.json; tail -3 gpurun_out/bench_ref_n2.err
+timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_node_ring.py -x -q 2>&1 | tail -3
