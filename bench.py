@@ -465,6 +465,7 @@ def run_b200(args):
       "hop": hop, "pipelined": pipelined, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+  ring.close()
   if n > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -108,6 +108,7 @@ def _worker(rank, world, port, q, mailbox):
   bids, _ = ring.generate_batch(np.arange(15, dtype=np.int32).reshape(3, 5), 4)
   q.put((rank, native.linked, tok, ids, native.calls[:n0], native.calls[n0:], None if bids is None else bids.tolist(), ring.step, ids_hop, hop_calls))
   dist.barrier()
+  ring.close()
   dist.destroy_process_group()
 
 

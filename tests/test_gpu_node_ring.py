@@ -31,9 +31,16 @@ def _oracle_ids(shape_name, prompt_ids, n_gen, sampler):
   return generate_ids([ref], np.asarray(prompt_ids, dtype=np.int32).reshape(1, -1), n_gen, sampler=sampler)
 
 
+def _ngpu():
+  import torch
+  return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
 @pytest.mark.skipif(reference_root() is None, reason="the reference package is neither under baseline/_ref nor at /root/reference")
-@pytest.mark.parametrize("device_hop", [True, False])
-def test_reference_node_ring_on_gpu_matches_oracle(tmp_path, monkeypatch, device_hop):
+@pytest.mark.parametrize("device_hop,devices", [(True, (0, 0)), (False, (0, 0)), (True, (0, 1))])
+def test_reference_node_ring_on_gpu_matches_oracle(tmp_path, monkeypatch, device_hop, devices):
+  if max(devices) >= _ngpu():
+    pytest.skip("needs 2 GPUs: the hop crosses NVLink (peer stores into the other GPU's HBM)")
   import_reference(monkeypatch, tmp_path)
   from unittest import mock
   from xotorch.orchestration.node import Node
@@ -50,7 +57,8 @@ def test_reference_node_ring_on_gpu_matches_oracle(tmp_path, monkeypatch, device
   caps = DeviceCapabilities(model="B200", chip="B200", memory=183359, flops=DeviceFlops(fp32=0, fp16=0, int8=0))
 
   async def run():
-    engines = [B200ShardInferenceEngine(LocalDirDownloader({NAME: d}), device=0) for _ in range(2)]
+    # node0 (last shard) on devices[0], node1 (first shard) on devices[1]
+    engines = [B200ShardInferenceEngine(LocalDirDownloader({NAME: d}), device=devices[i]) for i in range(2)]
     nodes = []
     for i, eng in enumerate(engines):
       server, discovery = mock.AsyncMock(), mock.AsyncMock()
@@ -98,12 +106,12 @@ def test_reference_node_ring_on_gpu_matches_oracle(tmp_path, monkeypatch, device
     e.native.close()
 
 
-def _pair(shape_name, split):
+def _pair(shape_name, split, devices=None):
   from xotorch_b200.native import NativeShard
   shape = PRESETS[shape_name]
   out = []
-  for a, b in split:
-    e = NativeShard(hf_config(shape), device=0)
+  for i, (a, b) in enumerate(split):
+    e = NativeShard(hf_config(shape), device=0 if devices is None else devices[i])
     e.set_shard(a, b)
     e.init_synthetic(1234)
     out.append(e)
@@ -113,12 +121,23 @@ def _pair(shape_name, split):
 @pytest.mark.parametrize("shape_name,split", [("tiny-llama-hd64", [(0, 1), (2, 3)]), ("tiny-llama-hd64", [(0, 0), (1, 2), (3, 3)]),
                                               ("tiny-llama-hd128-f16", [(0, 0), (1, 2)]), ("tiny-mixtral", [(0, 1), (2, 3)])])
 def test_forward_hop_equals_host_array_api(shape_name, split):
+  _hop_vs_host(shape_name, split, None)
+
+
+def test_forward_hop_across_two_gpus():
+  if _ngpu() < 2:
+    pytest.skip("needs 2 GPUs")
+  _hop_vs_host("tiny-llama-hd64", [(0, 1), (2, 3)], [0, 1])
+  _hop_vs_host("tiny-llama-hd128-f16", [(0, 0), (1, 2)], [1, 0])
+
+
+def _hop_vs_host(shape_name, split, devices):
   """xotb200_forward_hop (hidden state handed over by the producing kernel / one peer copy) == xotb200_forward (fp32 host
   arrays), bit for bit: a 150-token prompt (tensor-core prefill + peer copy), a 5-token chunk (decode kernel, multi-token hop)
   and single decode steps (fused inbox hop, consumer launched before the producer has finished)."""
   shape = PRESETS[shape_name]
   prompt = synth_prompt(shape.vocab, 150)
-  ref = _pair(shape_name, split)
+  ref = _pair(shape_name, split, devices)
   for e in ref:
     e.begin_request(220)
   want, x, pos = [], prompt.astype(np.int32), 0
@@ -129,7 +148,7 @@ def test_forward_hop_equals_host_array_api(shape_name, split):
       data = e.forward(data, pos)
     want.append(data.copy())
     pos += c.shape[1]
-  hop = _pair(shape_name, split)
+  hop = _pair(shape_name, split, devices)
   for i, e in enumerate(hop):
     e.begin_request(220)
     if i + 1 < len(hop):
