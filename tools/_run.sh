@@ -1,3 +1,3 @@
 set -x
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 4 --steps 2 --warmup 1 --model mixtral-8x7b > gpurun_out/bench_mixtral_n4.json 2> gpurun_out/bench_mixtral_n4.err; tail -c 3000 gpurun_out/bench_mixtral_n4.json; tail -3 gpurun_out/bench_mixtral_n4.err
-timeout 600 python -m pytest tests/test_gpu_node_ring.py tests/test_gpu_multi.py tests/test_gpu_scheduler.py -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_tc_prefill.py tests/test_gpu_parity.py tests/test_gpu_full_depth.py -x -q 2>&1 | tail -5
+for s in 512 1024 4096; do python tools/prefill_bench.py llama-3-8b $s 2>&1 | tail -1; XOTB200_TC_2SM=0 python tools/prefill_bench.py llama-3-8b $s 2>&1 | tail -1; done

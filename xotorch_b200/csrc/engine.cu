@@ -438,6 +438,29 @@ static int launch_tc_gemm_persistent(xotb200_engine* e, const CUtensorMap& tmA, 
   return 0;
 }
 
+// CTA-pair variant (cta_group::2): clusters of two CTAs, one 256-token x NT tile per pair; tmB is the weight map with a box of NT/2 rows
+template <int NT, int NS>
+static int launch_tc_gemm_2sm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const TcGemmArgs& a_in, int epi, cudaStream_t st) {
+  TcGemmArgs a = a_in;
+  a.err = &e->ctl->err;
+  void (*fn)(CUtensorMap, CUtensorMap, TcGemmArgs) = nullptr;
+  const bool f16 = e->cfg.dtype == XOTB200_DTYPE_F16;
+  switch (epi) {
+    case TCE_STORE: fn = f16 ? xb::fp::tc_gemm_2sm_kernel<NT, TCE_STORE, NS> : xb::bf::tc_gemm_2sm_kernel<NT, TCE_STORE, NS>; break;
+    case TCE_RESID: fn = f16 ? xb::fp::tc_gemm_2sm_kernel<NT, TCE_RESID, NS> : xb::bf::tc_gemm_2sm_kernel<NT, TCE_RESID, NS>; break;
+    case TCE_QKV: fn = f16 ? xb::fp::tc_gemm_2sm_kernel<NT, TCE_QKV, NS> : xb::bf::tc_gemm_2sm_kernel<NT, TCE_QKV, NS>; break;
+    case TCE_SWIGLU: fn = f16 ? xb::fp::tc_gemm_2sm_kernel<NT, TCE_SWIGLU, NS> : xb::bf::tc_gemm_2sm_kernel<NT, TCE_SWIGLU, NS>; break;
+    default: set_err("no CTA-pair GEMM for epilogue %d", epi); return XOTB200_EINVAL;
+  }
+  if (int rc = ensure_smem_attr(e->device, (const void*)fn, tc2_smem_bytes(NT, NS))) return rc;
+  const int total = ((a.S + 2 * TC_M - 1) / (2 * TC_M)) * (a.N / NT);
+  const int pairs = std::max(1, std::min(total, e->sm_count / 2));
+  fn<<<2 * pairs, TC_THREADS, tc2_smem_bytes(NT, NS), st>>>(tmA, tmB_half, a);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
 static int launch_tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmArgs& a_in, int epi, TcCfg c,
                           cudaStream_t st) {
   TcGemmArgs a = a_in;
@@ -533,6 +556,13 @@ static int prepare_tc(xotb200_engine* e, int n_tokens) {
 // one GEMM of the prefill: weight `widx` of the shard (see ensure_tm_w), tile configuration from (N, tokens in flight)
 static int tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, int widx, const TcGemmArgs& a, int epi, cudaStream_t st) {
   const TcCfg c = tc_cfg(a.N, epi == TCE_HEAD_LAST ? 1 : a.S);
+  // several 256-token tiles in flight and a 256-wide N tile: CTA pairs (each CTA stages half of the weight tile)
+  static const bool use_2sm = !(getenv("XOTB200_TC_2SM") && atoi(getenv("XOTB200_TC_2SM")) == 0);
+  if (use_2sm && epi != TCE_HEAD_LAST && a.tile_info == nullptr && a.mt0 == 0 && c.nt == 256 && a.S > 2 * TC_M && a.N % 256 == 0 &&
+      ((a.S + 2 * TC_M - 1) / (2 * TC_M)) * (a.N / 256) >= e->sm_count / 4) {
+    if (int rc = ensure_tm_w(e, 128)) return rc;
+    return launch_tc_gemm_2sm<256, 6>(e, tmA, e->tm_w[128][widx], a, epi, st);
+  }
   if (int rc = ensure_tm_w(e, c.nt)) return rc;
   return launch_tc_gemm(e, tmA, e->tm_w[c.nt][widx], a, epi, c, st);
 }

@@ -95,6 +95,62 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- CTA-pair (cta_group::2) forms: one 256 x NT tile per cluster of two CTAs.  Each CTA stages its own 128 rows of A and HALF
+//      of the B tile, the leader's single thread issues tcgen05.mma.cta_group::2 (reads both CTAs' shared memory, writes both
+//      CTAs' tensor memory), commits are multicast to the same mbarrier in both CTAs (forms as in CUTLASS
+//      cute/arch/{copy_sm100_tma,mma_sm100_umma,tmem_allocator_sm100}.hpp and cutlass/arch/barrier.h) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is counted on an mbarrier that may live in the PEER CTA (cluster address `bar_cluster`)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot_smem, int ncols) {   // one warp in EACH CTA of the pair, same slot offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, int ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// arrives on `bar` (same offset) in every CTA of `mask` once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__host__ __device__ constexpr int tc2_stage_bytes(int nt) { return TC_M * TC_BK * 2 + (nt / 2) * TC_BK * 2; }   // per CTA: own A rows + half of B
+__host__ __device__ constexpr int tc2_smem_bytes(int nt, int ns) { return ns * tc2_stage_bytes(nt) + 1024 + 256; }
+
 // ------------------------------------------------------------------------------------------------------------
 // row-parallel helpers around the GEMMs
 // ------------------------------------------------------------------------------------------------------------
