@@ -298,6 +298,7 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.x = e->x; a.q = e->q; a.attn_out = e->attn_out; a.act = e->act; a.logits = e->logits;
   a.part_ml = e->part_ml; a.part_acc = e->part_acc; a.tickets = e->tickets;
   a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit; a.nsplit_min = e->nsplit_min;
+  { static const int l2a = getenv("XOTB200_L2_AHEAD") ? atoi(getenv("XOTB200_L2_AHEAD")) : 0; a.l2_ahead = l2a; }
   a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
   a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
@@ -1412,7 +1413,8 @@ int xotb200_forward_hop(xotb200_engine* e, const int32_t* tokens, int64_t seq_in
   REQUIRE(n_tokens >= 1 && pos0 >= 0, "bad n_tokens/pos0");
   REQUIRE(e->L > 0, "begin_request was not called");
   REQUIRE(pos0 + n_tokens <= e->L, "KV cache overflow: pos0 %d + n %d > capacity %d", pos0, n_tokens, e->L);
-  REQUIRE(e->last ? (logits_f32 != nullptr) : (seq_out != nullptr && e->next_inbox != nullptr), e->last ? "null output" : "next engine not linked");
+  if (e->last) REQUIRE(logits_f32 != nullptr, "null output");
+  else REQUIRE(seq_out != nullptr && e->next_inbox != nullptr, "next engine not linked");
   if (int rc = xotb200_check_loaded(e)) return rc;
   CK(cudaSetDevice(e->device));
   if (int rc = ensure_staging(e, n_tokens)) return rc;
