@@ -298,7 +298,6 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.x = e->x; a.q = e->q; a.attn_out = e->attn_out; a.act = e->act; a.logits = e->logits;
   a.part_ml = e->part_ml; a.part_acc = e->part_acc; a.tickets = e->tickets;
   a.cta_best_val = e->cta_best_val; a.cta_best_idx = e->cta_best_idx; a.nsplit = e->nsplit; a.nsplit_min = e->nsplit_min;
-  { static const int l2a = getenv("XOTB200_L2_AHEAD") ? atoi(getenv("XOTB200_L2_AHEAD")) : 0; a.l2_ahead = l2a; }
   a.ctl = e->ctl; a.inbox = e->inbox; a.next_inbox = e->next_inbox; a.tokens_log = e->tokens_log;
   a.t_in = e->t_in; a.t_out = e->t_out; a.bar_counter = e->bar_counter;
   a.mode = mode; a.n_steps = n_steps; a.step0 = step0; a.pos0 = pos0;
