@@ -66,7 +66,6 @@ struct MegaArgs {
   unsigned int* tickets;     // [Hkv]
   float* cta_best_val;
   int* cta_best_idx;
-  int l2_ahead;             // experiment: stages of this CTA's tile list the producer prefetches into L2 while the ring is full (0 = off)
   int nsplit, nsplit_min;   // context splits per kv head: upper bound (CTAs / kv heads) and the count used for short contexts
   StepCtl* ctl;
   InboxHdr *inbox, *next_inbox;
