@@ -1,7 +1,4 @@
 set -x
-qb() { timeout 300 python tools/quick_bench.py llama-3-8b 128 512 0 > gpurun_out/qb_$1.log 2>&1; echo "=== $1"; grep -E '"iter": 2|^qkv  |^o  |^gu  |attention chain|step total|Error|error' gpurun_out/qb_$1.log | cut -c1-330; }
-export XOTB200_LIB=$PWD/xotorch_b200/lib/ab_l2a.so
-XOTB200_L2_AHEAD=0 qb l2a_0
-XOTB200_L2_AHEAD=4 qb l2a_4
-XOTB200_L2_AHEAD=12 qb l2a_12
-XOTB200_L2_AHEAD=24 qb l2a_24
+timeout 600 python -m pytest tests/test_gpu_tc_prefill.py -x -q 2>&1 | tail -3
+for s in 512 1024 4096; do python tools/prefill_bench.py llama-3-8b $s 2>&1 | tail -1; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_prefill1024_launches.csv python tools/prefill_bench.py llama-3-8b 1024 > gpurun_out/ncu_pf.log 2>&1; python tools/ncu_summarize.py launches gpurun_out/r2_prefill1024_launches.csv | head -8

@@ -560,6 +560,8 @@ static int tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, int widx, const Tc
   static const bool use_2sm = !(getenv("XOTB200_TC_2SM") && atoi(getenv("XOTB200_TC_2SM")) == 0);
   if (use_2sm && epi != TCE_HEAD_LAST && a.tile_info == nullptr && a.mt0 == 0 && c.nt == 256 && a.S > 2 * TC_M && a.N % 256 == 0 &&
       ((a.S + 2 * TC_M - 1) / (2 * TC_M)) * (a.N / 256) >= e->sm_count / 4) {
+    // (128-wide pair tiles for the narrow GEMMs — 2.6 waves instead of 1.3 for QKV — were measured SLOWER: 76 vs 62 us; the
+    //  256-wide tile's operand economy outweighs the partial wave)
     if (int rc = ensure_tm_w(e, 128)) return rc;
     return launch_tc_gemm_2sm<256, 6>(e, tmA, e->tm_w[128][widx], a, epi, st);
   }
