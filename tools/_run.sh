@@ -1,4 +1,6 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_tc_prefill.py -x -q 2>&1 | tail -3
-for s in 512 1024 4096; do python tools/prefill_bench.py llama-3-8b $s 2>&1 | tail -1; done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_prefill1024_launches.csv python tools/prefill_bench.py llama-3-8b 1024 > gpurun_out/ncu_pf.log 2>&1; python tools/ncu_summarize.py launches gpurun_out/r2_prefill1024_launches.csv | head -8
+qb() { timeout 300 python tools/quick_bench.py llama-3-8b 128 512 0 > gpurun_out/qb_$1.log 2>&1; echo "=== $1"; grep -E 'xotb200:|"iter": 2|^qkv  |attention chain|step total|Error|error' gpurun_out/qb_$1.log | cut -c1-330; }
+export XOTB200_LIB=$PWD/xotorch_b200/lib/ab_direct6.so
+XOTB200_KV_PERSIST=1 XOTB200_ATTN_DIRECT_MAX=0 qb d6_split_persist
+XOTB200_KV_PERSIST=1 XOTB200_ATTN_DIRECT_MAX=1024 qb d6_direct_persist
+XOTB200_KV_PERSIST=0 XOTB200_ATTN_DIRECT_MAX=1024 qb d6_direct
