@@ -1,6 +1,4 @@
 set -x
-qb() { timeout 300 python tools/quick_bench.py llama-3-8b 128 512 0 > gpurun_out/qb_$1.log 2>&1; echo "=== $1"; grep -E 'xotb200:|"iter": 2|^qkv  |attention chain|step total|Error|error' gpurun_out/qb_$1.log | cut -c1-330; }
-export XOTB200_LIB=$PWD/xotorch_b200/lib/ab_direct6.so
-XOTB200_KV_PERSIST=1 XOTB200_ATTN_DIRECT_MAX=0 qb d6_split_persist
-XOTB200_KV_PERSIST=1 XOTB200_ATTN_DIRECT_MAX=1024 qb d6_direct_persist
-XOTB200_KV_PERSIST=0 XOTB200_ATTN_DIRECT_MAX=1024 qb d6_direct
+qb() { timeout 300 python tools/quick_bench.py llama-3-8b 128 512 0 > gpurun_out/qb_$1.log 2>&1; echo "=== $1"; grep -E 'xotb200:|"iter": 2|^qkv  |^o  |^gu |^down|^head|attention chain|step total|Error|error|barrier of' gpurun_out/qb_$1.log | cut -c1-330; }
+XOTB200_PACE_GBS=7300 qb rel
+XOTB200_PACE_GBS=7300 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_node_ring.py -m gpu -x -q 2>&1 | tail -5

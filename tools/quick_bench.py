@@ -56,6 +56,11 @@ if len(sys.argv) > 4:   # timeline of one ring step
     row = stg[k]; row = row[row > 0]
     t0 = tl[20 + k, 1]
     print(names[k], "stage arrival (us after consume start):", [round((v - t0) / 1e3, 2) for v in row[:16]])
+  for k in range(4):     # grid barrier closing op k of layer 5: local arrival (all 9 warps) -> atomic issued -> all CTAs arrived
+    b = stg[k][40:45]
+    if b[0] > 0:
+      t2k = tl[20 + k, 2]
+      print(f"{names[k]:5s} barrier of layer 5: consumers done -> epilogue warp done {(b[4]-t2k)/1e3:5.2f} | -> CTA arrived {(b[0]-t2k)/1e3:5.2f} | atomic issued +{(b[1]-b[0])/1e3:4.2f} | all CTAs seen +{(b[2]-b[1])/1e3:4.2f} us")
   st = stg[0][48:54]; t2 = tl[20, 2]
   print("attention chain (layer 5, CTA %s): tiles done -> B1 exit %.2f | K/V+softmax loop %.2f | warp+smem merge, partial store %.2f | ticket %.2f | (last CTA) split merge %.2f | B2 %.2f us" % ((sys.argv[4],) + tuple(round(x / 1e3, 2) for x in [st[0] - t2, st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4]])))
   rr = stg[0][54:64]; rr = rr[rr > 0]

@@ -40,6 +40,18 @@
 #include "megakernel.cuh"
 #include "prefill_tc.cuh"
 
+// Decode GEMV inner loop: 1 = mma.sync tensor-core path (default), 0 = the round-1 packed-FFMA2 loop (kept for A/B builds:
+// make EXTRA=-DXB_GEMV_MMA=0).  XB_TILE_STAMPS=1 adds per-tile timestamps to the debug timeline (tools/quick_bench.py).
+#ifndef XB_GEMV_MMA
+#define XB_GEMV_MMA 1
+#endif
+#ifndef XOTB200_DEFAULT_PACE_GBS
+#define XOTB200_DEFAULT_PACE_GBS 7300.0
+#endif
+#ifndef XB_TILE_STAMPS
+#define XB_TILE_STAMPS 0
+#endif
+
 // The dtype-dependent helpers and kernels are compiled twice: xb::bf (bfloat16 weights) and xb::fp (IEEE half weights).
 namespace xb {
 namespace bf {
@@ -170,6 +182,9 @@ struct xotb200_engine {
   int mega_xbuf = 0, mega_grid = 0, mega_nstage = 0;
   int cta_limit = 0;
   // tensor-core prefill (prefill_tc.cuh)
+  int l2_ahead = 0;                // decode producer look-ahead into L2 (stages per CTA)
+  int max_inflight = 0;            // decode producer window (bulk copies in flight per CTA, 0 = ring depth)
+  unsigned int pace_q = 0;         // decode producer pacing, 2^-16 ns per byte per CTA (0 = off)
   bool tc_fuse = true;             // RoPE/KV-append and SwiGLU fused into GEMM epilogues (XOTB200_TC_FUSE=0: separate kernels, A/B)
   int prefill_mode = 0;            // 0 auto (TC when n_tokens >= 8), 1 always the decode kernel, 2 always TC
   bf16 *tc_x = nullptr, *tc_xn = nullptr, *tc_qkv = nullptr, *tc_q = nullptr, *tc_ao = nullptr, *tc_gu = nullptr, *tc_act = nullptr;
@@ -281,8 +296,16 @@ static int prepare_mega(xotb200_engine* e) {
   if (const char* v = getenv("XOTB200_NSPLIT")) e->nsplit = std::max(1, std::min(e->nsplit, atoi(v)));   // tuning hooks
   if (const char* v = getenv("XOTB200_NSPLIT_MIN")) e->nsplit_min = std::max(1, atoi(v));
   e->nsplit_min = std::min(e->nsplit_min, e->nsplit);
+  // producer pacing (see shard_step_kernel): target AGGREGATE weight-stream rate of the grid in GB/s, shared evenly by the CTAs
+  double pace_gbs = XOTB200_DEFAULT_PACE_GBS;
+  if (const char* v = getenv("XOTB200_PACE_GBS")) pace_gbs = atof(v);
+  if (const char* v = getenv("XOTB200_L2_AHEAD")) e->l2_ahead = std::max(0, atoi(v));
+  if (const char* v = getenv("XOTB200_INFLIGHT")) e->max_inflight = std::max(0, atoi(v));
+  e->pace_q = pace_gbs > 0 ? (unsigned int)(65536.0 * e->mega_grid / pace_gbs + 0.5) : 0u;
   return 0;
 }
+
+static size_t dbg_cap(const xotb200_engine* e) { return (size_t)(4 * e->cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8; }
 
 // Launch the persistent shard-step kernel for n_steps steps.  mode 0 = ring (inbox in, next inbox out),
 // mode 1 = direct (staging buffers).
@@ -311,11 +334,15 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.hop_in = mode == 1 ? e->hop_in : 0; a.hop_out = mode == 1 ? e->hop_out : 0;
   a.hop_seq_in = e->hop_seq_in; a.hop_seq_out = e->hop_seq_out;
   a.xbuf_bytes = e->mega_xbuf;
+  a.pace_q = e->pace_q;
+  a.max_inflight = e->max_inflight;
+  a.l2_ahead = e->l2_ahead;
   a.E = c.n_experts; a.topk = c.experts_per_tok;
   a.gu_stride = (size_t)2 * c.ffn * c.dim; a.dn_stride = (size_t)c.dim * c.ffn;
   a.layer_tab_bytes = c.n_layers * (int)sizeof(LayerDev);
   a.route_log = e->route_log;
   a.dbg = (mode == 0 && e->dbg_step >= 0) ? e->dbg : nullptr; a.dbg_step = e->dbg_step; a.dbg_cta = e->dbg_cta;
+  a.dbg_all = a.dbg ? e->dbg + dbg_cap(e) : nullptr;
   CK(cudaMemsetAsync(e->bar_counter, 0, 4, st));
   void* params[] = {&a};
   CK(cudaLaunchCooperativeKernel((const void*)e->mega, dim3(e->mega_grid), dim3(MK_THREADS), params, e->mega_smem, st));
@@ -1737,7 +1764,8 @@ int xotb200_debug_routing(xotb200_engine* e, int32_t* out, int n_positions) {
 int xotb200_debug_timeline(xotb200_engine* e, int step, int cta, uint64_t* out, int n_u64) {
   REQUIRE(e, "null engine");
   CK(cudaSetDevice(e->device));
-  const size_t cap = (size_t)(4 * e->cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8;
+  // [one CTA's timeline: dbg_cap words][every CTA: (4 * n_layers + 1) ops x 256 CTAs x 3 words]
+  const size_t cap = dbg_cap(e) + (size_t)(4 * e->cfg.n_layers + 1) * 256 * 3;
   if (!e->dbg) { CK(cudaMalloc(&e->dbg, cap * 8)); MEMSET_SYNC(e, e->dbg, 0, cap * 8); }
   if (out) {
     REQUIRE(n_u64 >= 0 && (size_t)n_u64 <= cap, "n_u64 too large (max %zu)", cap);

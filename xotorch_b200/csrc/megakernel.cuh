@@ -97,8 +97,12 @@ struct MegaArgs {
   int layer_tab_bytes;           // size of the shared-memory layer table (the MoE stash follows it)
   int* route_log;                // [L][nl] experts chosen for request 0 at (position, local layer): lo | hi << 8 (parity tests)
   int xbuf_bytes;            // shared-memory activation buffer size
+  int l2_ahead;              // producer look-ahead into L2 while the ring is full (stages, 0 = off), see the producer
+  int max_inflight;          // producer window: bulk copies issued and not yet landed (0 = the whole ring), see the producer
+  unsigned int pace_q;       // producer pacing: 2^-16 ns per byte of this CTA's weight stream (0 = unpaced), see the producer
   unsigned long long* dbg;   // optional timeline [n_ops+1][4] of CTA dbg_cta for step dbg_step (NULL = off)
   int dbg_step, dbg_cta;
+  unsigned long long* dbg_all;   // optional [n_ops][256][3]: (consume start, tiles done, landed stages) of EVERY CTA for step dbg_step
 };
 
 enum { OP_QKV = 0, OP_O = 1, OP_GU = 2, OP_DOWN = 3, OP_HEAD = 4 };

@@ -268,6 +268,8 @@ class NativeShard:
 
   def debug_timeline(self, step: int, cta: int = 0, read: bool = False):
     n = (4 * self.cfg.n_layers + 2) * 4 * 2 + 4 * 64 + 8
+    if read == "all":      # + every CTA's (consume start, tiles done, landed stages) per op: [4 * n_layers + 1][256][3]
+      n += (4 * self.cfg.n_layers + 1) * 256 * 3
     if read:
       out = np.zeros(n, dtype=np.uint64)
       check(self.lib.xotb200_debug_timeline(self.h, int(step), int(cta), out.ctypes.data_as(C.c_void_p), n))
