@@ -139,9 +139,6 @@ struct xotb200_engine {
   int rope_len = 0;
   // activations / scratch
   bf16 *x = nullptr, *q = nullptr, *attn_out = nullptr, *act = nullptr;
-  uint2* ll_x = nullptr;           // LL exchange buffers of the decode kernel (megakernel_impl.inc) and the running sequence number
-  uint32_t* ll_act = nullptr;
-  unsigned int ll_seq = 0;
   float* logits = nullptr;
   float *part_ml = nullptr, *part_acc = nullptr;
   unsigned int* tickets = nullptr;  // [Hkv] attention + [1] step end
@@ -337,9 +334,6 @@ static int launch_mega(xotb200_engine* e, int mode, int n_steps, int step0, int 
   a.hop_in = mode == 1 ? e->hop_in : 0; a.hop_out = mode == 1 ? e->hop_out : 0;
   a.hop_seq_in = e->hop_seq_in; a.hop_seq_out = e->hop_seq_out;
   a.xbuf_bytes = e->mega_xbuf;
-  a.ll_x = e->ll_x; a.ll_act = e->ll_act;
-  a.ll_seq0 = e->ll_seq;
-  e->ll_seq += (unsigned int)n_steps * (unsigned int)(4 * a.nl + 1);   // every op of every step of this launch gets its own number
   a.pace_q = e->pace_q;
   a.max_inflight = e->max_inflight;
   a.l2_ahead = e->l2_ahead;
@@ -960,10 +954,6 @@ int xotb200_create(const xotb200_model_cfg* cfg, int device, xotb200_engine** ou
   CK(cudaMalloc(&e->q, (size_t)Hq * hd * 2));
   CK(cudaMalloc(&e->attn_out, (size_t)Hq * hd * 2));
   CK(cudaMalloc(&e->act, (size_t)cfg->ffn * 2 * (cfg->n_experts > 0 ? 2 : 1)));   // MoE: both selected experts' activations
-  CK(cudaMalloc(&e->ll_x, (size_t)2 * (D / 2) * 8));
-  MEMSET_SYNC(e, e->ll_x, 0, (size_t)2 * (D / 2) * 8);
-  CK(cudaMalloc(&e->ll_act, (size_t)2 * (cfg->n_experts > 0 ? 2 : 1) * cfg->ffn * 4));
-  MEMSET_SYNC(e, e->ll_act, 0, (size_t)2 * (cfg->n_experts > 0 ? 2 : 1) * cfg->ffn * 4);
   CK(cudaMalloc(&e->logits, (size_t)cfg->vocab * 4));
   CK(cudaMalloc(&e->part_ml, (size_t)Hq * e->nsplit * 2 * 4));
   CK(cudaMalloc(&e->part_acc, (size_t)Hq * e->nsplit * hd * 4));
@@ -1012,7 +1002,7 @@ int xotb200_destroy(xotb200_engine* e) {
   for (bf16* p : e->hop_buf)
     if (p) cudaFree(p);
   if (e->tok_count_host) cudaFreeHost(const_cast<unsigned int*>(e->tok_count_host));
-  void* ptrs[] = {e->ll_x, e->ll_act, e->d_req_map, e->d_pos_tab, e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
+  void* ptrs[] = {e->d_req_map, e->d_pos_tab, e->x, e->q, e->attn_out, e->act, e->logits, e->part_ml, e->part_acc, e->tickets, e->cta_best_val,
                   e->cta_best_idx, e->ctl, e->bar_counter, e->dbg, e->inbox, e->tokens_log, e->t_in, e->t_out, e->rope, e->stage_tokens,
                   e->stage_f32, e->stage_in, e->stage_out};
   for (void* p : ptrs)

@@ -97,10 +97,6 @@ struct MegaArgs {
   int layer_tab_bytes;           // size of the shared-memory layer table (the MoE stash follows it)
   int* route_log;                // [L][nl] experts chosen for request 0 at (position, local layer): lo | hi << 8 (parity tests)
   int xbuf_bytes;            // shared-memory activation buffer size
-  // Flagged activation exchange (see "LL exchange" in megakernel_impl.inc): the vectors every CTA reads at an op boundary
-  uint2* ll_x;               // [2][D/2]: (two 16-bit values of the residual stream, 32-bit sequence number) per row pair
-  uint32_t* ll_act;          // [2][nseg * F]: 16-bit SwiGLU value | 16-bit tag << 16
-  unsigned int ll_seq0;      // sequence number of (step 0, op 0) of this launch; op `o` of step `s` writes seq0 + s * n_ops + o + 1
   int l2_ahead;              // producer look-ahead into L2 while the ring is full (stages, 0 = off), see the producer
   int max_inflight;          // producer window: bulk copies issued and not yet landed (0 = the whole ring), see the producer
   unsigned int pace_q;       // producer pacing: 2^-16 ns per byte of this CTA's weight stream (0 = unpaced), see the producer
