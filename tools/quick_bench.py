@@ -9,7 +9,12 @@ from xotorch_b200.native import NativeShard
 name = sys.argv[1] if len(sys.argv) > 1 else "llama-3-8b"
 n_prompt = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 n_gen = int(sys.argv[3]) if len(sys.argv) > 3 else 512
-shape = PRESETS[name]
+if ":" in name:      # "llama-3-70b:8" = that preset cut to its first 8 layers (fits one GPU; per-layer behaviour is what is measured)
+  import dataclasses
+  base, nl = name.split(":")
+  shape = dataclasses.replace(PRESETS[base], n_layers=int(nl), name=f"{base}-{nl}l")
+else:
+  shape = PRESETS[name]
 t = time.time()
 e = NativeShard(hf_config(shape), 0)
 e.set_shard(0, shape.n_layers - 1)
