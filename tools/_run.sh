@@ -1,3 +1,4 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_node_ring.py tests/test_gpu_scheduler.py -m gpu -x -q 2>&1 | tail -4
-bash tools/_run_multi.sh 2
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tc_ -c 700 --csv --log-file gpurun_out/r2b_prefill128_launches.csv python tools/prefill_bench.py llama-3-8b 128 > gpurun_out/ncu_prefill128.log 2>&1
+tail -3 gpurun_out/ncu_prefill128.log
+wc -l gpurun_out/r2b_prefill128_launches.csv

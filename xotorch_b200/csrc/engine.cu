@@ -185,6 +185,9 @@ struct xotb200_engine {
   int l2_ahead = 0;                // decode producer look-ahead into L2 (stages per CTA)
   int max_inflight = 0;            // decode producer window (bulk copies in flight per CTA, 0 = ring depth)
   unsigned int pace_q = 0;         // decode producer pacing, 2^-16 ns per byte per CTA (0 = off)
+  float* tc_ws = nullptr;          // split-K partial tiles of the one-tile prefill GEMMs, and their tickets
+  size_t tc_ws_bytes = 0;
+  unsigned int* tc_ws_ticket = nullptr;
   bool tc_fuse = true;             // RoPE/KV-append and SwiGLU fused into GEMM epilogues (XOTB200_TC_FUSE=0: separate kernels, A/B)
   int prefill_mode = 0;            // 0 auto (TC when n_tokens >= 8), 1 always the decode kernel, 2 always TC
   bf16 *tc_x = nullptr, *tc_xn = nullptr, *tc_qkv = nullptr, *tc_q = nullptr, *tc_ao = nullptr, *tc_gu = nullptr, *tc_act = nullptr;
@@ -440,7 +443,7 @@ static int launch_tc_gemm_nt(xotb200_engine* e, const CUtensorMap& tmA, const CU
   }
   if (int rc = ensure_smem_attr(e->device, (const void*)fn, tc_smem_bytes(NT, NS))) return rc;
   const int mtiles = a.grid_m > 0 ? a.grid_m : (epi == TCE_HEAD_LAST ? 1 : (a.S + TC_M - 1) / TC_M - a.mt0);
-  fn<<<dim3(mtiles, a.N / NT), TC_THREADS, tc_smem_bytes(NT, NS), st>>>(tmA, tmB, a);
+  fn<<<dim3(mtiles, a.N / NT, a.ksplit > 1 ? a.ksplit : 1), TC_THREADS, tc_smem_bytes(NT, NS), st>>>(tmA, tmB, a);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -583,6 +586,35 @@ static int prepare_tc(xotb200_engine* e, int n_tokens) {
 // one GEMM of the prefill: weight `widx` of the shard (see ensure_tm_w), tile configuration from (N, tokens in flight)
 static int tc_gemm(xotb200_engine* e, const CUtensorMap& tmA, int widx, const TcGemmArgs& a, int epi, cudaStream_t st) {
   const TcCfg c = tc_cfg(a.N, epi == TCE_HEAD_LAST ? 1 : a.S);
+  // ONE token tile (S <= 128): the GEMM streams the weight once and is bound by how many SMs pull on it.  N / NT tiles
+  // of the narrow GEMMs (O, down: 32 tiles of 128; QKV: 48) leave most SMs idle and every CTA re-reads the whole [128, K]
+  // activation tile; split-K puts ksplit CTAs on each tile, each reading only its K slice of both operands.
+  static const bool use_splitk = !(getenv("XOTB200_TC_SPLITK") && atoi(getenv("XOTB200_TC_SPLITK")) == 0);
+  if (use_splitk && a.S <= TC_M && a.mt0 == 0 && a.tile_info == nullptr && a.N % 128 == 0 &&
+      (epi == TCE_STORE || epi == TCE_RESID || epi == TCE_QKV)) {
+    const int tiles = a.N / 128, nkb = a.K / TC_BK;
+    int ks = std::min(4, e->sm_count / std::max(1, tiles));
+    while (ks > 1 && nkb % ks != 0) --ks;
+    if (ks >= 2 && nkb / ks >= 4) {
+      const size_t need = (size_t)tiles * ks * TC_M * 128 * 4;
+      if (need > e->tc_ws_bytes) {
+        CK(cudaStreamSynchronize(st));
+        if (e->tc_ws) CK(cudaFree(e->tc_ws));
+        e->tc_ws = nullptr;
+        CK(cudaMalloc(&e->tc_ws, need));
+        e->tc_ws_bytes = need;
+      }
+      if (!e->tc_ws_ticket) {
+        CK(cudaMalloc(&e->tc_ws_ticket, 4096 * 4));
+        MEMSET_SYNC(e, e->tc_ws_ticket, 0, 4096 * 4);
+      }
+      REQUIRE(tiles <= 4096, "split-K ticket table too small for N=%d", a.N);
+      if (int rc = ensure_tm_w(e, 128)) return rc;
+      TcGemmArgs b = a;
+      b.ksplit = ks; b.ws = e->tc_ws; b.ws_ticket = e->tc_ws_ticket; b.err = &e->ctl->err;
+      return launch_tc_gemm_nt<128, 6>(e, tmA, e->tm_w[128][widx], b, epi, st);
+    }
+  }
   // several 256-token tiles in flight and a 256-wide N tile: CTA pairs (each CTA stages half of the weight tile)
   static const bool use_2sm = !(getenv("XOTB200_TC_2SM") && atoi(getenv("XOTB200_TC_2SM")) == 0);
   if (use_2sm && epi != TCE_HEAD_LAST && a.tile_info == nullptr && a.mt0 == 0 && c.nt == 256 && a.S > 2 * TC_M && a.N % 256 == 0 &&
@@ -995,7 +1027,7 @@ int xotb200_destroy(xotb200_engine* e) {
   cudaDeviceSynchronize();
   free_shard(e);
   if (e->next_ipc && e->next_inbox) cudaIpcCloseMemHandle(e->next_inbox);
-  void* tcp[] = {e->tc_x, e->tc_xn, e->tc_qkv, e->tc_q, e->tc_ao, e->tc_gu, e->tc_act, e->moe_xg, e->moe_gu, e->moe_act, e->moe_y,
+  void* tcp[] = {e->tc_ws, e->tc_ws_ticket, e->tc_x, e->tc_xn, e->tc_qkv, e->tc_q, e->tc_ao, e->tc_gu, e->tc_act, e->moe_xg, e->moe_gu, e->moe_act, e->moe_y,
                  e->moe_route_e, e->moe_route_w, e->moe_row_of, e->moe_row_token, e->moe_exp_info};
   for (void* p : tcp)
     if (p) cudaFree(p);

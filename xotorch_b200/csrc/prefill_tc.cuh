@@ -41,6 +41,12 @@ struct TcGemmArgs {
   bf16 *kc, *vc;          // K / V cache of (request, layer): [Hkv][L][hd]
   const float2* rope;     // [L][hd/2] (cos, sin)
   int q_rows, kv_rows, hd, L, pos0;
+  // split-K (one 128-token tile: the GEMM is weight-streaming bound and N / NT tiles do not fill the GPU): grid.z = ksplit CTAs
+  // share an output tile, each sweeps K / ksplit; fp32 partial tiles go through `ws`, the CTA drawing the last ticket of the tile
+  // adds them in split order (deterministic) and runs the epilogue
+  int ksplit;             // 1 = off
+  float* ws;              // [tile][ksplit][128][NT] fp32
+  unsigned int* ws_ticket;   // [tile], zero between launches (the last CTA resets its entry)
   int* err;               // sticky device error word (StepCtl::err): 3 = a bounded wait of the persistent GEMM expired
 };
 
