@@ -48,6 +48,9 @@
 #ifndef XOTB200_DEFAULT_PACE_GBS
 #define XOTB200_DEFAULT_PACE_GBS 7300.0
 #endif
+#ifndef XB_GEMV_PAIRS
+#define XB_GEMV_PAIRS 0
+#endif
 #ifndef XB_TILE_STAMPS
 #define XB_TILE_STAMPS 0
 #endif
